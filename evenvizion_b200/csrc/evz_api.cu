@@ -1,0 +1,70 @@
+// Handle lifetime, error text and scratch management of libevz.so.
+#include "evz_common.cuh"
+
+static char g_create_err[512] = "";
+
+extern "C" int evz_version(void) { return EVZ_VERSION; }
+
+extern "C" int evz_create(int device, evz_handle** out) {
+    if (!out) return EVZ_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        snprintf(g_create_err, sizeof(g_create_err), "evz_create: no CUDA device (%s); this library has no CPU fallback",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return EVZ_E_NODEVICE;
+    }
+    if (device < 0 || device >= n) {
+        snprintf(g_create_err, sizeof(g_create_err), "evz_create: device %d out of range [0,%d)", device, n);
+        return EVZ_E_ARG;
+    }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        snprintf(g_create_err, sizeof(g_create_err), "evz_create: %s", cudaGetErrorString(e));
+        return EVZ_E_CUDA;
+    }
+    if (prop.major != 10) {
+        snprintf(g_create_err, sizeof(g_create_err), "evz_create: device %d is sm_%d%d; libevz is built for sm_100a (B200) only",
+                 device, prop.major, prop.minor);
+        return EVZ_E_UNSUPPORTED;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        snprintf(g_create_err, sizeof(g_create_err), "evz_create: cudaSetDevice: %s", cudaGetErrorString(e));
+        return EVZ_E_CUDA;
+    }
+    evz_handle* h = new evz_handle();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    return EVZ_OK;
+}
+
+extern "C" void evz_destroy(evz_handle* h) {
+    if (!h) return;
+    if (h->scratch) cudaFree(h->scratch);
+    delete h;
+}
+
+extern "C" const char* evz_last_error(const evz_handle* h) { return h ? h->err : g_create_err; }
+
+extern "C" int evz_sm_count(const evz_handle* h) { return h ? h->sm_count : 0; }
+
+int evz_scratch(evz_handle* h, size_t bytes, void** out) {
+    if (bytes > h->scratch_bytes) {
+        // growing is the one place the library synchronises: work queued on the old block must finish
+        EVZ_CUDA_CHECK(h, cudaDeviceSynchronize());
+        if (h->scratch) { cudaFree(h->scratch); h->scratch = nullptr; h->scratch_bytes = 0; }
+        const size_t want = evz_align_up(bytes + bytes / 4, size_t(1) << 20);
+        cudaError_t e = cudaMalloc(&h->scratch, want);
+        if (e != cudaSuccess) {
+            EVZ_SET_ERR(h, "scratch allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+            return EVZ_E_NOMEM;
+        }
+        h->scratch_bytes = want;
+    }
+    *out = h->scratch;
+    return EVZ_OK;
+}

@@ -1,0 +1,43 @@
+// Shared host-side plumbing of libevz.so: handle, error reporting, scratch.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "../../include/evz.h"
+
+typedef CUresult (*evz_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+struct evz_handle {
+    int device = 0;
+    int sm_count = 0;
+    char err[512] = {0};
+    // grow-only scratch
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    // cached TMA descriptor of the descriptor store
+    CUtensorMap tmap;
+    const void* tmap_ptr = nullptr;
+    int64_t tmap_rows = 0;
+    evz_encode_tiled_fn encode = nullptr;
+    bool match_attr_set = false;
+};
+
+#define EVZ_SET_ERR(h, ...) do { if (h) snprintf((h)->err, sizeof((h)->err), __VA_ARGS__); } while (0)
+
+#define EVZ_CUDA_CHECK(h, expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) {            \
+        EVZ_SET_ERR(h, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));        \
+        return EVZ_E_CUDA; } } while (0)
+
+#define EVZ_LAUNCH_CHECK(h) EVZ_CUDA_CHECK(h, cudaGetLastError())
+
+#define EVZ_REQUIRE(h, cond, msg) do { if (!(cond)) { EVZ_SET_ERR(h, "%s: %s", __func__, msg); return EVZ_E_ARG; } } while (0)
+
+// returns a device scratch region of at least `bytes` (256-byte aligned); contents undefined
+int evz_scratch(evz_handle* h, size_t bytes, void** out);
+
+static inline size_t evz_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

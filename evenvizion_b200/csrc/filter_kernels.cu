@@ -1,0 +1,275 @@
+// Ingest (descriptor pack, norms/ckey, coordinate canonical ids) and K1b/K2
+// (Lowe ratio test, many-to-one filter, coordinate de-dup, ordered compaction, gather).
+// Byte/integer work bound by memory traffic: one CTA per frame / per pair, coalesced row
+// accesses, per-pair tables in shared memory.
+#include "evz_common.cuh"
+#include <climits>
+
+namespace evz {
+
+constexpr int kMaxKpSmem = 12288;   // per-frame keypoint limit of the shared-memory tables
+
+__device__ __forceinline__ unsigned long long coord_key(float x, float y) {
+    // Python dict keys (x, y): 0.0 and -0.0 are the same key
+    const unsigned int bx = x == 0.f ? 0u : __float_as_uint(x);
+    const unsigned int by = y == 0.f ? 0u : __float_as_uint(y);
+    return (static_cast<unsigned long long>(bx) << 32) | by;
+}
+__device__ __forceinline__ unsigned int hash64(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+    return static_cast<unsigned int>(k);
+}
+
+// one CTA per frame: pack descriptor rows to 128 zero-padded bytes, ckey, coords; zero the padding rows
+__global__ void __launch_bounds__(256)
+ingest_pack_kernel(const void* __restrict__ raw_desc, int raw_is_f32, int d,
+                   const float* __restrict__ raw_coords, const int64_t* __restrict__ raw_off,
+                   const int32_t* __restrict__ row_off,
+                   uint8_t* __restrict__ desc, int32_t* __restrict__ ckey, float* __restrict__ coords,
+                   int32_t* __restrict__ bad_count) {
+    const int f = blockIdx.x;
+    const int64_t r0 = raw_off[f];
+    const int n = static_cast<int>(raw_off[f + 1] - r0);
+    const int p0 = row_off[f], p1 = row_off[f + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int bad = 0;
+    for (int i = warp; i < p1 - p0; i += nwarps) {
+        const int64_t prow = static_cast<int64_t>(p0) + i;
+        unsigned int packed = 0;
+        if (i < n && lane * 4 < d) {
+            if (raw_is_f32) {
+                const float* src = static_cast<const float*>(raw_desc) + (r0 + i) * d + lane * 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (lane * 4 + j < d) {
+                        const float v = src[j];
+                        const float r = rintf(v);
+                        if (!(v == r) || v < 0.f || v > 255.f) ++bad;
+                        packed |= (static_cast<unsigned int>(fminf(fmaxf(r, 0.f), 255.f)) & 255u) << (8 * j);
+                    }
+                }
+            } else {
+                const uint8_t* src = static_cast<const uint8_t*>(raw_desc) + (r0 + i) * d + lane * 4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (lane * 4 + j < d) packed |= static_cast<unsigned int>(src[j]) << (8 * j);
+            }
+        }
+        reinterpret_cast<unsigned int*>(desc + prow * EVZ_DESC_BYTES)[lane] = packed;
+        unsigned int s = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const unsigned int b = (packed >> (8 * j)) & 255u; s += b * b; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffff, s, o);
+        if (lane == 0) ckey[prow] = i < n ? static_cast<int32_t>((s << 8) | static_cast<unsigned int>(prow & 255)) : INT_MAX;
+        if (lane < 2) coords[prow * 2 + lane] = i < n ? raw_coords[(r0 + i) * 2 + lane] : 0.f;
+    }
+    if (bad) atomicAdd(bad_count, bad);
+}
+
+// one CTA per frame: canon[i] = smallest keypoint index of the frame with the same (x, y)
+__global__ void __launch_bounds__(256)
+ingest_canon_kernel(const float* __restrict__ coords, const int64_t* __restrict__ raw_off,
+                    const int32_t* __restrict__ row_off, int32_t* __restrict__ canon, int table_size) {
+    extern __shared__ int32_t table[];
+    const int f = blockIdx.x;
+    const int n = static_cast<int>(raw_off[f + 1] - raw_off[f]);
+    const int p0 = row_off[f], p1 = row_off[f + 1];
+    const float2* c = reinterpret_cast<const float2*>(coords) + p0;
+    int cap = 64;
+    while (cap < 2 * n) cap <<= 1;
+    cap = min(cap, table_size);
+    const unsigned int mask = cap - 1;
+    for (int i = threadIdx.x; i < cap; i += blockDim.x) table[i] = -1;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float2 ci = c[i];
+        const unsigned long long key = coord_key(ci.x, ci.y);
+        unsigned int s = hash64(key) & mask;
+        while (true) {
+            int cur = table[s];
+            if (cur < 0) {
+                cur = atomicCAS(&table[s], -1, i);
+                if (cur < 0) break;
+            }
+            const float2 cc = c[cur];
+            if (coord_key(cc.x, cc.y) == key) { atomicMin(&table[s], i); break; }
+            s = (s + 1) & mask;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < p1 - p0; i += blockDim.x) {
+        int out = -1;
+        if (i < n) {
+            const float2 ci = c[i];
+            const unsigned long long key = coord_key(ci.x, ci.y);
+            unsigned int s = hash64(key) & mask;
+            while (true) {
+                const int cur = table[s];
+                const float2 cc = c[cur];
+                if (coord_key(cc.x, cc.y) == key) { out = cur; break; }
+                s = (s + 1) & mask;
+            }
+        }
+        canon[p0 + i] = out;
+    }
+}
+
+// block-wide exclusive scan of one int per thread (blockDim.x <= 1024); returns the exclusive
+// prefix and the block total
+__device__ __forceinline__ int block_excl_scan(int v, int* warp_sums, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffff, incl, d); if (lane >= d) incl += t; }
+    __syncthreads();
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nwarps ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffff, w, d); if (lane >= d) w += t; }
+        warp_sums[lane] = w;
+    }
+    __syncthreads();
+    total = warp_sums[nwarps - 1];
+    return incl - v + (warp > 0 ? warp_sums[warp - 1] : 0);
+}
+
+struct FilterArgs {
+    const int32_t* top2_idx; const int32_t* top2_d2;
+    const float* coords; const int32_t* canon;
+    const int32_t* row_off; const int32_t* n_kp;
+    const int32_t* pair_q; const int32_t* pair_t; const int32_t* out_off;
+    double ratio; int min_matching_pts;
+    uint8_t* surv; int32_t* m_idx; float* m_pts; int32_t* m_cnt; int32_t* n_filtered; int32_t* status;
+};
+
+// one CTA per pair
+__global__ void __launch_bounds__(512)
+filter_matches_kernel(const FilterArgs a) {
+    extern __shared__ int32_t fsm[];
+    __shared__ int warp_sums[32];
+    __shared__ int kept_total;
+    const int p = blockIdx.x;
+    const int qf = a.pair_q[p], tf = a.pair_t[p];
+    const int nq = a.n_kp[qf], nt = a.n_kp[tf];
+    const int q0 = a.row_off[qf], t0 = a.row_off[tf];
+    const int64_t o0 = a.out_off[p];
+    int32_t* tsel = fsm;              // [nq] claimed train index of a surviving query, else -1
+    int32_t* first_c = tsel + nq;     // [nq] smallest kept query of a coordinate group
+    int32_t* last_c = first_c + nq;   // [nq] largest kept query of a coordinate group
+    int32_t* cnt_t = last_c + nq;     // [nt] surviving queries per train index
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) { first_c[i] = INT_MAX; last_c[i] = -1; }
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) cnt_t[i] = 0;
+    if (threadIdx.x == 0) kept_total = 0;
+    __syncthreads();
+    // Lowe ratio test: matches[0].distance < matches[1].distance * ratio, f32 sqrt, double compare
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+        const int2 id = reinterpret_cast<const int2*>(a.top2_idx)[o0 + q];
+        const int2 dd = reinterpret_cast<const int2*>(a.top2_d2)[o0 + q];
+        bool s = false;
+        if (id.y >= 0) {
+            const double d0 = static_cast<double>(__fsqrt_rn(static_cast<float>(dd.x)));
+            const double d1 = static_cast<double>(__fsqrt_rn(static_cast<float>(dd.y)));
+            s = d0 < __dmul_rn(d1, a.ratio);
+        }
+        tsel[q] = s ? id.x : -1;
+        if (a.surv) a.surv[o0 + q] = s ? 1 : 0;
+        if (s) atomicAdd(&cnt_t[id.x], 1);
+    }
+    __syncthreads();
+    // many-to-one filter, then group the kept queries by coordinate
+    int kept = 0;
+    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+        int t = tsel[q];
+        if (t >= 0 && cnt_t[t] != 1) { t = -1; tsel[q] = -1; }
+        if (t >= 0) {
+            ++kept;
+            const int c = a.canon[q0 + q];
+            atomicMin(&first_c[c], q);
+            atomicMax(&last_c[c], q);
+        }
+    }
+    if (kept) atomicAdd(&kept_total, kept);
+    __syncthreads();
+    const int n_filtered = kept_total;
+    const bool ok = n_filtered >= a.min_matching_pts;
+    // ordered compaction: first position of every coordinate group, value of its last member
+    int base = 0;
+    const float2* cq = reinterpret_cast<const float2*>(a.coords) + q0;
+    const float2* ct = reinterpret_cast<const float2*>(a.coords) + t0;
+    for (int qb = 0; qb < nq; qb += blockDim.x) {
+        const int q = qb + threadIdx.x;
+        int emit = 0, c = 0;
+        if (ok && q < nq && tsel[q] >= 0) { c = a.canon[q0 + q]; emit = first_c[c] == q; }
+        int total;
+        const int pos = base + block_excl_scan(emit, warp_sums, total);
+        if (emit) {
+            const int t = tsel[last_c[c]];
+            const float2 pa = cq[q], pb = ct[t];
+            reinterpret_cast<int2*>(a.m_idx)[o0 + pos] = make_int2(q, t);
+            reinterpret_cast<float4*>(a.m_pts)[o0 + pos] = make_float4(pa.x, pa.y, pb.x, pb.y);
+        }
+        base += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        a.m_cnt[p] = ok ? base : 0;
+        a.n_filtered[p] = n_filtered;
+        a.status[p] = ok ? EVZ_ST_OK : EVZ_ST_FEW_MATCHES;
+    }
+}
+
+}  // namespace evz
+
+extern "C" int evz_ingest(evz_handle* h, const void* raw_desc, int raw_is_f32, int d,
+                          const float* raw_coords, const int64_t* raw_off, const int32_t* row_off, int n_frames,
+                          uint8_t* desc, int32_t* ckey, float* coords, int32_t* canon, int32_t* bad_count,
+                          void* stream) {
+    if (!h) return EVZ_E_ARG;
+    EVZ_REQUIRE(h, raw_desc && raw_coords && raw_off && row_off && desc && ckey && coords && canon && bad_count, "null pointer");
+    EVZ_REQUIRE(h, d > 0 && d <= EVZ_DESC_BYTES && d % 4 == 0, "descriptor width must be a multiple of 4, at most 128");
+    if (n_frames <= 0) return EVZ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    evz::ingest_pack_kernel<<<n_frames, 256, 0, st>>>(raw_desc, raw_is_f32, d, raw_coords, raw_off, row_off, desc, ckey, coords, bad_count);
+    EVZ_LAUNCH_CHECK(h);
+    const int table = 32768;    // >= 2 * kMaxKpSmem
+    static bool attr = false;
+    if (!attr) {
+        EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::ingest_canon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, table * 4));
+        attr = true;
+    }
+    evz::ingest_canon_kernel<<<n_frames, 256, table * 4, st>>>(coords, raw_off, row_off, canon, table);
+    EVZ_LAUNCH_CHECK(h);
+    return EVZ_OK;
+}
+
+extern "C" int evz_filter_matches(evz_handle* h, const int32_t* top2_idx, const int32_t* top2_d2,
+                                  const float* coords, const int32_t* canon,
+                                  const int32_t* row_off, const int32_t* n_kp,
+                                  const int32_t* pair_q, const int32_t* pair_t, const int32_t* out_off, int n_pairs,
+                                  int max_kp, double ratio, int min_matching_pts,
+                                  uint8_t* surv, int32_t* m_idx, float* m_pts, int32_t* m_cnt,
+                                  int32_t* n_filtered, int32_t* status, void* stream) {
+    if (!h) return EVZ_E_ARG;
+    EVZ_REQUIRE(h, top2_idx && top2_d2 && coords && canon && row_off && n_kp && pair_q && pair_t && out_off &&
+                   m_idx && m_pts && m_cnt && n_filtered && status, "null pointer");
+    if (max_kp > evz::kMaxKpSmem) {
+        EVZ_SET_ERR(h, "evz_filter_matches: max_kp %d exceeds the supported %d keypoints per frame", max_kp, evz::kMaxKpSmem);
+        return EVZ_E_UNSUPPORTED;
+    }
+    if (n_pairs <= 0) return EVZ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int smem = 16 * (max_kp > 0 ? max_kp : 1);
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::filter_matches_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    evz::FilterArgs a{top2_idx, top2_d2, coords, canon, row_off, n_kp, pair_q, pair_t, out_off, ratio, min_matching_pts,
+                      surv, m_idx, m_pts, m_cnt, n_filtered, status};
+    evz::filter_matches_kernel<<<n_pairs, 512, smem, st>>>(a);
+    EVZ_LAUNCH_CHECK(h);
+    return EVZ_OK;
+}

@@ -1,0 +1,487 @@
+// K3 + K4: seeded RANSAC homography and Levenberg-Marquardt refit, one CTA per frame pair.
+// Replaces cv2.findHomography(a, b, cv2.RANSAC, thresh) (reference matching.py:156-157,
+// utils.py:356-358) and the 70 % gate of compute_homography (utils.py:359-360).
+//
+//   phase 1  every thread owns kHpt hypotheses at a time: counter-based PCG sample of 4 distinct
+//            matches, closed-form 4-point solve in f64 registers (projective basis), cast to f32;
+//   phase 2  all matches (float4 ax,ay,bx,by staged in shared memory) are scored against the
+//            thread's hypotheses: broadcast LDS.128, OpenCV's f32 computeError formula with
+//            individually rounded operations (explicit _rn intrinsics, IEEE reciprocal), inlier
+//            count in a register; block arg-max on (count desc, hypothesis asc);
+//   phase 3  inlier mask of the winner (warp ballot), then LM on the 8 free parameters in f64
+//            with OpenCV's damping schedule, started from the winning model;
+//   phase 4  final mask = f32 error of the refined H <= thresh^2, inlier count, 70 % gate.
+//
+// This file is compiled with --fmad=false: the f64 solver must round exactly like the NumPy
+// oracle (oracle/ransac.py) so that identical seeds give bit-identical inlier masks.
+#include "evz_common.cuh"
+#include <cfloat>
+
+namespace evz {
+
+constexpr int kRsThreads = 256;
+constexpr int kHpt = 4;           // hypotheses scored concurrently per thread
+constexpr int kLmMaxIters = 20;   // OpenCV uses 10 from a DLT start; we start from the 4-point model
+constexpr int kNSums = 32;        // 21 JtJ + 8 Jtr + S + max|r| (+1 pad)
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16; return x;
+}
+__device__ __forceinline__ uint32_t pcg_next(uint32_t& s) {
+    s = s * 747796405u + 2891336453u;
+    const uint32_t w = ((s >> ((s >> 28) + 4u)) ^ s) * 277803737u;
+    return (w >> 22) ^ w;
+}
+// 4 distinct indices in [0, m), m >= 4 (oracle/ransac.py hyp_indices)
+__device__ __forceinline__ void sample4(uint32_t seed, uint32_t pair_level, uint32_t hyp, int m, int (&idx)[4]) {
+    uint32_t s = mix32(seed ^ mix32(pair_level + 0x9E3779B9u));
+    s = mix32(s + hyp * 0x9E3779B9u);
+    int sorted[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t r = pcg_next(s);
+        int c = static_cast<int>(__umulhi(r, static_cast<uint32_t>(m - k)));
+#pragma unroll
+        for (int j = 0; j < k; ++j) c += (c >= sorted[j]);
+        idx[k] = c;
+        // insert into the sorted prefix
+        int v = c;
+#pragma unroll
+        for (int j = 0; j < k; ++j) { if (v < sorted[j]) { const int t = sorted[j]; sorted[j] = v; v = t; } }
+        sorted[k] = v;
+    }
+}
+
+__device__ __forceinline__ double area2(double ax, double ay, double bx, double by, double cx, double cy) {
+    return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+}
+
+// closed-form homography through 4 correspondences (oracle/ransac.py solve4, same operation order)
+__device__ __forceinline__ bool solve4(const float4 (&p)[4], double (&H)[9]) {
+    const double x0 = p[0].x, y0 = p[0].y, u0 = p[0].z, v0 = p[0].w;
+    const double x1 = p[1].x, y1 = p[1].y, u1 = p[1].z, v1 = p[1].w;
+    const double x2 = p[2].x, y2 = p[2].y, u2 = p[2].z, v2 = p[2].w;
+    const double x3 = p[3].x, y3 = p[3].y, u3 = p[3].z, v3 = p[3].w;
+    const double l0 = area2(x3, y3, x1, y1, x2, y2);
+    const double l1 = area2(x0, y0, x3, y3, x2, y2);
+    const double l2 = area2(x0, y0, x1, y1, x3, y3);
+    const double lt = area2(x0, y0, x1, y1, x2, y2);
+    const double m0 = area2(u3, v3, u1, v1, u2, v2);
+    const double m1 = area2(u0, v0, u3, v3, u2, v2);
+    const double m2 = area2(u0, v0, u1, v1, u3, v3);
+    const double mt = area2(u0, v0, u1, v1, u2, v2);
+    const double eps = 1e-6;
+    const int neg = (lt * mt < 0) + (l0 * m0 < 0) + (l1 * m1 < 0) + (l2 * m2 < 0);
+    const bool big = fabs(lt) > eps && fabs(l0) > eps && fabs(l1) > eps && fabs(l2) > eps &&
+                     fabs(mt) > eps && fabs(m0) > eps && fabs(m1) > eps && fabs(m2) > eps;
+    bool ok = big && (neg == 0 || neg == 4);
+    const double w0 = m0 * (l1 * l2);
+    const double w1 = m1 * (l0 * l2);
+    const double w2 = m2 * (l0 * l1);
+    const double c0[3] = {y1 - y2, x2 - x1, x1 * y2 - y1 * x2};
+    const double c1[3] = {y2 - y0, x0 - x2, x2 * y0 - y2 * x0};
+    const double c2[3] = {y0 - y1, x1 - x0, x0 * y1 - y0 * x1};
+    const double q0[3] = {u0, v0, 1.0}, q1[3] = {u1, v1, 1.0}, q2[3] = {u2, v2, 1.0};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double a0 = w0 * q0[r], a1 = w1 * q1[r], a2 = w2 * q2[r];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) H[3 * r + j] = (a0 * c0[j] + a1 * c1[j]) + a2 * c2[j];
+    }
+    const double inv = 1.0 / H[8];
+    ok = ok && isfinite(inv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) H[i] = H[i] * inv;
+    H[8] = 1.0;
+    return ok;
+}
+
+// OpenCV HomographyEstimatorCallback::computeError, f32, no contraction
+__device__ __forceinline__ float reproj_err32(const float (&h)[8], const float4 p) {
+    const float den = __fadd_rn(__fadd_rn(__fmul_rn(h[6], p.x), __fmul_rn(h[7], p.y)), 1.f);
+    const float ww = __frcp_rn(den);
+    const float dx = __fsub_rn(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(h[0], p.x), __fmul_rn(h[1], p.y)), h[2]), ww), p.z);
+    const float dy = __fsub_rn(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(h[3], p.x), __fmul_rn(h[4], p.y)), h[5]), ww), p.w);
+    return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+}
+
+// matrix_H_prev pre-transform of compute_homography (utils.py:351-355): f64 map, f32 result
+__device__ __forceinline__ float2 pre_map(const double* T, float x, float y) {
+    const double X = (T[0] * x + T[1] * y) + T[2];
+    const double Y = (T[3] * x + T[4] * y) + T[5];
+    const double W = (T[6] * x + T[7] * y) + T[8];
+    return make_float2(static_cast<float>(X / W), static_cast<float>(Y / W));
+}
+
+struct FhArgs {
+    const float* pts; const int32_t* off; const int32_t* cnt;
+    const double* pre_H;
+    int n_hyp; uint32_t seed; int64_t pair_id_base; int level;
+    float thresh2; double min_inlier_frac; int fail_status;
+    int32_t* status; double* H; uint8_t* mask; int32_t* inl_cnt;
+    int32_t* best_hyp; int32_t* best_cnt; uint8_t* mask_best; double* H_best;
+    int max_cnt;
+};
+
+// 8x8 SPD solve by Gaussian elimination with partial pivoting (robust to the semi-definite corner)
+__device__ bool solve8(const double* A /*sym full 8x8*/, const double* b, double* x) {
+    double M[8][9];
+    for (int i = 0; i < 8; ++i) { for (int j = 0; j < 8; ++j) M[i][j] = A[i * 8 + j]; M[i][8] = b[i]; }
+    for (int c = 0; c < 8; ++c) {
+        int piv = c; double best = fabs(M[c][c]);
+        for (int r = c + 1; r < 8; ++r) if (fabs(M[r][c]) > best) { best = fabs(M[r][c]); piv = r; }
+        if (!(best > 0.0)) return false;
+        if (piv != c) for (int j = c; j < 9; ++j) { const double t = M[c][j]; M[c][j] = M[piv][j]; M[piv][j] = t; }
+        const double inv = 1.0 / M[c][c];
+        for (int r = c + 1; r < 8; ++r) {
+            const double f = M[r][c] * inv;
+            for (int j = c; j < 9; ++j) M[r][j] -= f * M[c][j];
+        }
+    }
+    for (int i = 7; i >= 0; --i) {
+        double s = M[i][8];
+        for (int j = i + 1; j < 8; ++j) s -= M[i][j] * x[j];
+        x[i] = s / M[i][i];
+    }
+    return true;
+}
+
+// index of (i, j), i <= j, in the packed accumulators described in lm_accumulate
+//   sums[0..5]   P  = sum p p^T            (p = (Mx ww, My ww, ww)) : 00 01 02 11 12 22
+//   sums[6..11]  Px = sum -xi p p2^T       (3 x 2)                   : 00 01 10 11 20 21
+//   sums[12..17] Py = sum -yi p p2^T       (3 x 2)
+//   sums[18..20] Q  = sum (xi^2+yi^2) p2 p2^T                         : 00 01 11
+//   sums[21..23] sum p rx, [24..26] sum p ry, [27..28] sum -(xi rx + yi ry) p2
+//   sums[29] S = sum r^2, sums[30] = max |r|
+__device__ __forceinline__ void lm_point(const double* h, const float4 pt, double* s) {
+    const double Mx = pt.x, My = pt.y;
+    double ww = h[6] * Mx + h[7] * My + 1.0;
+    ww = fabs(ww) > DBL_EPSILON ? 1.0 / ww : 0.0;
+    const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
+    const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
+    const double rx = xi - pt.z, ry = yi - pt.w;
+    const double p0 = Mx * ww, p1 = My * ww, p2 = ww;
+    s[0] += p0 * p0; s[1] += p0 * p1; s[2] += p0 * p2; s[3] += p1 * p1; s[4] += p1 * p2; s[5] += p2 * p2;
+    s[6] -= xi * p0 * p0; s[7] -= xi * p0 * p1; s[8] -= xi * p1 * p0; s[9] -= xi * p1 * p1; s[10] -= xi * p2 * p0; s[11] -= xi * p2 * p1;
+    s[12] -= yi * p0 * p0; s[13] -= yi * p0 * p1; s[14] -= yi * p1 * p0; s[15] -= yi * p1 * p1; s[16] -= yi * p2 * p0; s[17] -= yi * p2 * p1;
+    const double e = xi * xi + yi * yi;
+    s[18] += e * p0 * p0; s[19] += e * p0 * p1; s[20] += e * p1 * p1;
+    s[21] += p0 * rx; s[22] += p1 * rx; s[23] += p2 * rx;
+    s[24] += p0 * ry; s[25] += p1 * ry; s[26] += p2 * ry;
+    const double g = xi * rx + yi * ry;
+    s[27] -= g * p0; s[28] -= g * p1;
+    s[29] += rx * rx + ry * ry;
+    s[30] = fmax(s[30], fmax(fabs(rx), fabs(ry)));
+}
+// expand packed sums to the full symmetric 8x8 JtJ and Jtr
+__device__ void lm_expand(const double* s, double* A, double* v) {
+    for (int i = 0; i < 64; ++i) A[i] = 0.0;
+    const int tri[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+        A[i * 8 + j] = s[tri[i][j]];
+        A[(3 + i) * 8 + 3 + j] = s[tri[i][j]];
+    }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 2; ++j) {
+        A[i * 8 + 6 + j] = s[6 + 2 * i + j];        A[(6 + j) * 8 + i] = s[6 + 2 * i + j];
+        A[(3 + i) * 8 + 6 + j] = s[12 + 2 * i + j]; A[(6 + j) * 8 + 3 + i] = s[12 + 2 * i + j];
+    }
+    A[6 * 8 + 6] = s[18]; A[6 * 8 + 7] = s[19]; A[7 * 8 + 6] = s[19]; A[7 * 8 + 7] = s[20];
+    for (int i = 0; i < 3; ++i) { v[i] = s[21 + i]; v[3 + i] = s[24 + i]; }
+    v[6] = s[27]; v[7] = s[28];
+}
+
+struct LmShared {
+    double x[8], xd[8], d[8], A[64], v[8], D[8];
+    double S, lam, lc;
+    double sums[kNSums];
+    double wsum[kRsThreads / 32][kNSums];
+    int iter, go;
+};
+
+// all threads: accumulate the packed sums at parameters h over the inliers flagged in msk
+__device__ void lm_accumulate(const double* h, const float4* pts, const uint8_t* msk, int m, LmShared& L) {
+    double s[kNSums];
+#pragma unroll
+    for (int i = 0; i < kNSums; ++i) s[i] = 0.0;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) if (msk[i]) lm_point(h, pts[i], s);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 31; ++i) {
+        double t = s[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double u = __shfl_xor_sync(0xffffffff, t, o);
+            t = (i == 30) ? fmax(t, u) : t + u;
+        }
+        s[i] = t;
+    }
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 31; ++i) L.wsum[warp][i] = s[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < 31) {
+        double t = L.wsum[0][threadIdx.x];
+        for (int w = 1; w < kRsThreads / 32; ++w)
+            t = (threadIdx.x == 30) ? fmax(t, L.wsum[w][threadIdx.x]) : t + L.wsum[w][threadIdx.x];
+        L.sums[threadIdx.x] = t;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kRsThreads, 2)
+find_homography_kernel(const FhArgs a) {
+    extern __shared__ __align__(16) uint8_t fh_smem[];
+    float4* pts = reinterpret_cast<float4*>(fh_smem);
+    uint8_t* msk = fh_smem + static_cast<size_t>(a.max_cnt) * 16;
+    __shared__ LmShared L;
+    __shared__ double Hbest[9];
+    __shared__ unsigned long long red[kRsThreads / 32];
+    __shared__ int s_flag, s_cnt;
+
+    const int p = blockIdx.x;
+    if (a.status[p] != EVZ_ST_OK) return;
+    const int m = a.cnt[p];
+    const int64_t o = a.off[p];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (m < 4) { if (tid == 0) a.status[p] = EVZ_ST_FEW_POINTS; return; }
+
+    // stage the point pairs (optionally through matrix_H_prev)
+    const double* T = a.pre_H ? a.pre_H + static_cast<size_t>(p) * 9 : nullptr;
+    for (int i = tid; i < m; i += blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(a.pts)[o + i];
+        if (T) {
+            const float2 pa = pre_map(T, v.x, v.y), pb = pre_map(T, v.z, v.w);
+            v = make_float4(pa.x, pa.y, pb.x, pb.y);
+        }
+        pts[i] = v;
+    }
+    __syncthreads();
+
+    const uint32_t pair_level = static_cast<uint32_t>((a.pair_id_base + p) * 2 + a.level);
+    int best_h = -1, best_c = 0;
+    if (m == 4) {
+        // findHomography: npoints == 4 -> exact model through the 4 points, mask = ones, no LM
+        if (tid == 0) {
+            const float4 q[4] = {pts[0], pts[1], pts[2], pts[3]};
+            double H[9];
+            solve4(q, H);
+            bool fin = true;
+            for (int i = 0; i < 9; ++i) { Hbest[i] = H[i]; fin = fin && isfinite(H[i]); }
+            s_flag = fin;
+        }
+        __syncthreads();
+        if (!s_flag) { if (tid == 0) a.status[p] = a.fail_status; return; }
+        if (tid < 4) { if (a.mask_best) a.mask_best[o + tid] = 1; if (a.mask) a.mask[o + tid] = 1; }
+        if (tid == 0) {
+            for (int i = 0; i < 9; ++i) { a.H[static_cast<size_t>(p) * 9 + i] = Hbest[i]; if (a.H_best) a.H_best[static_cast<size_t>(p) * 9 + i] = Hbest[i]; }
+            if (a.best_hyp) a.best_hyp[p] = -1;
+            if (a.best_cnt) a.best_cnt[p] = 4;
+            if (a.inl_cnt) a.inl_cnt[p] = 4;
+        }
+        return;
+    }
+
+    // ---------------- phases 1 + 2: hypotheses
+    for (int h0 = 0; h0 < a.n_hyp; h0 += kRsThreads * kHpt) {
+        float hf[kHpt][8];
+        bool okh[kHpt];
+        int cnt[kHpt];
+#pragma unroll
+        for (int j = 0; j < kHpt; ++j) {
+            const int hyp = h0 + j * kRsThreads + tid;
+            cnt[j] = 0;
+            okh[j] = false;
+            if (hyp < a.n_hyp) {
+                int idx[4];
+                sample4(a.seed, pair_level, static_cast<uint32_t>(hyp), m, idx);
+                const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
+                double H[9];
+                okh[j] = solve4(q, H);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hf[j][i] = static_cast<float>(H[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hf[j][i] = 0.f;
+            }
+        }
+        for (int i = 0; i < m; ++i) {
+            const float4 pt = pts[i];
+#pragma unroll
+            for (int j = 0; j < kHpt; ++j) cnt[j] += (reproj_err32(hf[j], pt) <= a.thresh2) ? 1 : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < kHpt; ++j) {
+            const int hyp = h0 + j * kRsThreads + tid;
+            const int c = okh[j] ? cnt[j] : 0;
+            // this thread visits its hypotheses in ascending order: strict > keeps the lowest index
+            if (hyp < a.n_hyp && c > best_c) { best_c = c; best_h = hyp; }
+        }
+    }
+    // block arg-max on (count desc, hypothesis asc): pack count high, ~hyp low
+    unsigned long long key = best_h < 0 ? 0ull
+        : (static_cast<unsigned long long>(static_cast<uint32_t>(best_c)) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(best_h));
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) { const unsigned long long u = __shfl_xor_sync(0xffffffff, key, of); key = u > key ? u : key; }
+    if (lane == 0) red[warp] = key;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long k = red[0];
+        for (int w = 1; w < kRsThreads / 32; ++w) k = red[w] > k ? red[w] : k;
+        const int bc = static_cast<int>(k >> 32);
+        const int bh = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(k & 0xFFFFFFFFu));
+        s_cnt = bc;
+        s_flag = bh;
+        if (bc >= 4) {
+            int idx[4];
+            sample4(a.seed, pair_level, static_cast<uint32_t>(bh), m, idx);
+            const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
+            double H[9];
+            solve4(q, H);
+            for (int i = 0; i < 9; ++i) Hbest[i] = H[i];
+        }
+    }
+    __syncthreads();
+    const int bcnt = s_cnt, bhyp = s_flag;
+    if (tid == 0) { if (a.best_hyp) a.best_hyp[p] = bhyp; if (a.best_cnt) a.best_cnt[p] = bcnt; }
+    if (bcnt < 4) { if (tid == 0) a.status[p] = a.fail_status; return; }
+    if (tid == 0 && a.H_best) for (int i = 0; i < 9; ++i) a.H_best[static_cast<size_t>(p) * 9 + i] = Hbest[i];
+
+    // ---------------- phase 3: winner's inlier mask, then LM refit on it
+    {
+        float hb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hb[i] = static_cast<float>(Hbest[i]);
+        for (int i = tid; i < m; i += blockDim.x) {
+            const uint8_t in = reproj_err32(hb, pts[i]) <= a.thresh2 ? 1 : 0;
+            msk[i] = in;
+            if (a.mask_best) a.mask_best[o + i] = in;
+        }
+    }
+    __syncthreads();
+    if (tid < 8) L.x[tid] = Hbest[tid];
+    __syncthreads();
+    lm_accumulate(L.x, pts, msk, m, L);
+    if (tid == 0) {
+        lm_expand(L.sums, L.A, L.v);
+        for (int i = 0; i < 8; ++i) L.D[i] = L.A[i * 8 + i];
+        L.S = L.sums[29];
+        L.lam = 1.0; L.lc = 0.75; L.iter = 0;
+        L.go = L.sums[30] >= static_cast<double>(FLT_EPSILON);
+    }
+    __syncthreads();
+    while (L.go) {
+        if (tid == 0) {
+            double Ap[64];
+            for (int i = 0; i < 64; ++i) Ap[i] = L.A[i];
+            for (int i = 0; i < 8; ++i) Ap[i * 8 + i] += L.lam * L.D[i];
+            double d[8];
+            if (!solve8(Ap, L.v, d)) for (int i = 0; i < 8; ++i) d[i] = 0.0;
+            for (int i = 0; i < 8; ++i) { L.d[i] = d[i]; L.xd[i] = L.x[i] - d[i]; }
+        }
+        __syncthreads();
+        lm_accumulate(L.xd, pts, msk, m, L);
+        if (tid == 0) {
+            const double Sd = L.sums[29];
+            double dS = 0.0, tdv = 0.0, dmax = 0.0;
+            for (int i = 0; i < 8; ++i) {
+                double Ad = 0.0;
+                for (int j = 0; j < 8; ++j) Ad += L.A[i * 8 + j] * L.d[j];
+                dS += L.d[i] * (2.0 * L.v[i] - Ad);
+                tdv += L.d[i] * L.v[i];
+                dmax = fmax(dmax, fabs(L.d[i]));
+            }
+            const double R = (L.S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1.0);
+            if (R > 0.75) {
+                L.lam *= 0.5;
+                if (L.lam < L.lc) L.lam = 0.0;
+            } else if (R < 0.25) {
+                double nu = (Sd - L.S) / (fabs(tdv) > DBL_EPSILON ? tdv : 1.0) + 2.0;
+                nu = fmin(fmax(nu, 2.0), 10.0);
+                if (L.lam == 0.0) {
+                    // lambda = lc = 1 / max |diag(A^-1)|
+                    double maxval = DBL_EPSILON;
+                    for (int c = 0; c < 8; ++c) {
+                        double e[8], col[8];
+                        for (int i = 0; i < 8; ++i) e[i] = i == c ? 1.0 : 0.0;
+                        if (solve8(L.A, e, col)) maxval = fmax(maxval, fabs(col[c]));
+                    }
+                    L.lam = L.lc = 1.0 / maxval;
+                    nu *= 0.5;
+                }
+                L.lam *= nu;
+            }
+            double rmax = 0.0;
+            if (Sd < L.S) {
+                L.S = Sd;
+                for (int i = 0; i < 8; ++i) L.x[i] = L.xd[i];
+                lm_expand(L.sums, L.A, L.v);
+                rmax = L.sums[30];
+            } else {
+                rmax = 1.0;     // residual at the kept x is unchanged and was >= eps
+            }
+            L.iter++;
+            L.go = L.iter < kLmMaxIters && dmax >= static_cast<double>(FLT_EPSILON) && rmax >= static_cast<double>(FLT_EPSILON);
+        }
+        __syncthreads();
+    }
+
+    // ---------------- phase 4: final mask under the refined H, count, gate
+    float hfin[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hfin[i] = static_cast<float>(L.x[i]);
+    int c = 0;
+    for (int i = tid; i < m; i += blockDim.x) {
+        const int in = reproj_err32(hfin, pts[i]) <= a.thresh2 ? 1 : 0;
+        if (a.mask) a.mask[o + i] = static_cast<uint8_t>(in);
+        c += in;
+    }
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) c += __shfl_xor_sync(0xffffffff, c, of);
+    __syncthreads();
+    if (lane == 0) red[warp] = static_cast<unsigned long long>(c);
+    __syncthreads();
+    if (tid == 0) {
+        int tot = 0;
+        for (int w = 0; w < kRsThreads / 32; ++w) tot += static_cast<int>(red[w]);
+        if (a.inl_cnt) a.inl_cnt[p] = tot;
+        for (int i = 0; i < 8; ++i) a.H[static_cast<size_t>(p) * 9 + i] = L.x[i];
+        a.H[static_cast<size_t>(p) * 9 + 8] = 1.0;
+        if (a.min_inlier_frac > 0.0 && static_cast<double>(tot) < a.min_inlier_frac * static_cast<double>(m))
+            a.status[p] = EVZ_ST_FEW_INLIERS;
+    }
+}
+
+}  // namespace evz
+
+extern "C" int evz_find_homography(evz_handle* h, const float* pts, const int32_t* off, const int32_t* cnt, int n_pairs,
+                                   int max_cnt, const double* pre_H, int n_hyp, uint32_t seed, int64_t pair_id_base, int level,
+                                   double thresh, double min_inlier_frac, int fail_status,
+                                   int32_t* status, double* H, uint8_t* mask, int32_t* inl_cnt,
+                                   int32_t* best_hyp, int32_t* best_cnt, uint8_t* mask_best, double* H_best,
+                                   void* stream) {
+    if (!h) return EVZ_E_ARG;
+    EVZ_REQUIRE(h, pts && off && cnt && status && H, "null pointer");
+    EVZ_REQUIRE(h, n_hyp > 0, "n_hyp must be positive");
+    EVZ_REQUIRE(h, (reinterpret_cast<uintptr_t>(pts) & 15) == 0, "pts must be 16-byte aligned");
+    if (max_cnt > EVZ_MAX_KP) {
+        EVZ_SET_ERR(h, "evz_find_homography: max_cnt %d exceeds the supported %d points per pair", max_cnt, EVZ_MAX_KP);
+        return EVZ_E_UNSUPPORTED;
+    }
+    if (n_pairs <= 0) return EVZ_OK;
+    if (max_cnt < 4) max_cnt = 4;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int smem = max_cnt * 17 + 16;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::find_homography_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    const float t = static_cast<float>(thresh * thresh);
+    evz::FhArgs a{pts, off, cnt, pre_H, n_hyp, seed, pair_id_base, level, t, min_inlier_frac, fail_status,
+                  status, H, mask, inl_cnt, best_hyp, best_cnt, mask_best, H_best, max_cnt};
+    evz::find_homography_kernel<<<n_pairs, evz::kRsThreads, smem, st>>>(a);
+    EVZ_LAUNCH_CHECK(h);
+    return EVZ_OK;
+}

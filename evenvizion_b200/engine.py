@@ -1,0 +1,301 @@
+"""GeometryEngine: batched frame-to-frame geometry on one B200 through libevz.so.
+
+PyTorch is used for device memory, streams and (in distributed.py) NCCL; every kernel is
+hand-written CUDA behind the C ABI of include/evz.h.  All heavy results stay on the device
+as torch tensors; `video_geometry` is the host-arrays-in / host-arrays-out call.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EVZ_ROW_ALIGN, EVZ_DESC_BYTES, EVZ_MAX_KP
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+@dataclass
+class FrameStore:
+    """Device-resident frame store in the layout of include/evz.h."""
+    desc: torch.Tensor        # u8  [rows,128]
+    ckey: torch.Tensor        # i32 [rows]
+    coords: torch.Tensor      # f32 [rows,2]
+    canon: torch.Tensor       # i32 [rows]
+    row_off: torch.Tensor     # i32 [F+1] (device)
+    n_kp: torch.Tensor        # i32 [F]   (device)
+    row_off_h: np.ndarray     # host copies
+    n_kp_h: np.ndarray
+    d: int = 128
+    keep: tuple = ()          # staging buffers kept alive until the stream has consumed them
+
+    @property
+    def n_frames(self):
+        return len(self.n_kp_h)
+
+    @property
+    def rows(self):
+        return int(self.row_off_h[-1])
+
+    @property
+    def max_kp(self):
+        return int(self.n_kp_h.max()) if len(self.n_kp_h) else 0
+
+
+@dataclass
+class PairResults:
+    """Everything the per-pair pipeline produces (device tensors; per-row arrays are indexed
+    from out_off[p])."""
+    pair_q: torch.Tensor
+    pair_t: torch.Tensor
+    out_off: torch.Tensor
+    top2_idx: torch.Tensor
+    top2_d2: torch.Tensor
+    surv: torch.Tensor
+    m_idx: torch.Tensor
+    m_pts: torch.Tensor
+    m_cnt: torch.Tensor
+    n_filtered: torch.Tensor
+    status: torch.Tensor
+    H1: Optional[torch.Tensor] = None
+    mask1: Optional[torch.Tensor] = None
+    mask1_best: Optional[torch.Tensor] = None
+    best_hyp1: Optional[torch.Tensor] = None
+    best_cnt1: Optional[torch.Tensor] = None
+    inl1: Optional[torch.Tensor] = None
+    static_pts: Optional[torch.Tensor] = None
+    static_cnt: Optional[torch.Tensor] = None
+    static_r: Optional[torch.Tensor] = None
+    flags: Optional[torch.Tensor] = None
+    H: Optional[torch.Tensor] = None         # RANSAC #2 result = compute_homography's matrix
+    mask2: Optional[torch.Tensor] = None
+    mask2_best: Optional[torch.Tensor] = None
+    best_hyp2: Optional[torch.Tensor] = None
+    best_cnt2: Optional[torch.Tensor] = None
+    inl2: Optional[torch.Tensor] = None
+    extra: dict = field(default_factory=dict)
+
+
+class GeometryEngine:
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("evenvizion_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)           # make sure the primary context exists
+        h = C.c_void_p()
+        rc = self.lib.evz_create(device, C.byref(h))
+        if rc != 0:
+            raise _lib.EvzError(self.lib.evz_last_error(None).decode())
+        self.h = h
+        self.sm_count = self.lib.evz_sm_count(self.h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.evz_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        _lib.check(self.h, rc)
+
+    def _empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    @staticmethod
+    def layout(n_kp):
+        """row_off (int32 [F+1]) for per-frame keypoint counts: every frame starts at a multiple of 256."""
+        n_kp = np.asarray(n_kp, np.int64)
+        padded = (n_kp + EVZ_ROW_ALIGN - 1) // EVZ_ROW_ALIGN * EVZ_ROW_ALIGN
+        padded = np.maximum(padded, EVZ_ROW_ALIGN)
+        row_off = np.zeros(len(n_kp) + 1, np.int64)
+        np.cumsum(padded, out=row_off[1:])
+        if row_off[-1] >= 2 ** 31:
+            raise ValueError("frame store exceeds 2^31 rows; shard the video")
+        return row_off.astype(np.int32)
+
+    # ------------------------------------------------------------------ ingest
+    def ingest(self, desc, coords, n_kp=None, check=True) -> FrameStore:
+        """desc: [sum n_kp, d] uint8 or float32 (integer-valued, <= 255), frames concatenated (a
+        uniform [F, N, d] array is accepted too); coords: matching [.., 2] float32; n_kp: per-frame
+        counts.  Arrays may be numpy, pinned/CPU torch or CUDA torch tensors."""
+        desc_t = torch.as_tensor(desc)
+        coords_t = torch.as_tensor(coords)
+        if desc_t.dim() == 3:
+            f, n, d = desc_t.shape
+            if n_kp is None:
+                n_kp = np.full(f, n, np.int64)
+            desc_t = desc_t.reshape(f * n, d)
+            coords_t = coords_t.reshape(f * n, 2)
+        if n_kp is None:
+            raise ValueError("n_kp is required for concatenated input")
+        n_kp_h = np.asarray(n_kp, np.int64)
+        if int(n_kp_h.sum()) != desc_t.shape[0] or coords_t.shape[0] != desc_t.shape[0]:
+            raise ValueError("n_kp does not add up to the number of descriptor rows")
+        if len(n_kp_h) and int(n_kp_h.max()) > EVZ_MAX_KP:
+            raise ValueError(f"at most {EVZ_MAX_KP} keypoints per frame are supported")
+        d = int(desc_t.shape[1]) if desc_t.dim() == 2 and desc_t.shape[0] else 128
+        if d > EVZ_DESC_BYTES or d % 4:
+            raise ValueError("descriptor width must be a multiple of 4 and at most 128")
+        if desc_t.dtype == torch.uint8:
+            is_f32 = 0
+        elif desc_t.dtype == torch.float32:
+            is_f32 = 1
+        else:
+            raise TypeError("descriptors must be uint8 or float32 (SIFT/ORB); SURF's non-integer floats are not supported")
+        desc_d = desc_t.to(self.device, non_blocking=True).contiguous()
+        coords_d = coords_t.to(torch.float32).to(self.device, non_blocking=True).contiguous()
+        row_off_h = self.layout(n_kp_h)
+        raw_off_h = np.zeros(len(n_kp_h) + 1, np.int64)
+        np.cumsum(n_kp_h, out=raw_off_h[1:])
+        rows = int(row_off_h[-1])
+        raw_off = torch.from_numpy(raw_off_h).to(self.device, non_blocking=True)
+        row_off = torch.from_numpy(row_off_h).to(self.device, non_blocking=True)
+        n_kp_d = torch.from_numpy(n_kp_h.astype(np.int32)).to(self.device, non_blocking=True)
+        bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+        st = FrameStore(desc=self._empty((rows, EVZ_DESC_BYTES), torch.uint8), ckey=self._empty((rows,), torch.int32),
+                        coords=self._empty((rows, 2), torch.float32), canon=self._empty((rows,), torch.int32),
+                        row_off=row_off, n_kp=n_kp_d, row_off_h=row_off_h, n_kp_h=n_kp_h.astype(np.int32), d=d,
+                        keep=(desc_d, coords_d, raw_off, bad))
+        if rows and desc_d.shape[0]:
+            self._check(self.lib.evz_ingest(self.h, _ptr(desc_d), is_f32, d, _ptr(coords_d), _ptr(raw_off), _ptr(row_off),
+                                            len(n_kp_h), _ptr(st.desc), _ptr(st.ckey), _ptr(st.coords), _ptr(st.canon),
+                                            _ptr(bad), self._stream()))
+        elif rows:
+            st.desc.zero_(); st.ckey.fill_(2 ** 31 - 1); st.coords.zero_(); st.canon.fill_(-1)
+        if is_f32 and check and int(bad.item()):
+            raise ValueError(f"{int(bad.item())} descriptor values are not integers in [0,255]; "
+                             "the int8 tensor-core matcher is exact only for SIFT/ORB-style descriptors")
+        return st
+
+    # ------------------------------------------------------------------ K1 / K1b / K2
+    def match(self, st: FrameStore, pair_q, pair_t, ratio=0.5, min_matching_pts=4) -> PairResults:
+        pq = torch.as_tensor(pair_q, dtype=torch.int32).to(self.device)
+        pt = torch.as_tensor(pair_t, dtype=torch.int32).to(self.device)
+        P = int(pq.numel())
+        out_off = st.row_off[:-1][pq.long()].contiguous()
+        rows = st.rows
+        top2_idx = self._empty((rows, 2), torch.int32)
+        top2_d2 = self._empty((rows, 2), torch.int32)
+        self._check(self.lib.evz_match_top2(self.h, _ptr(st.desc), _ptr(st.ckey), rows, _ptr(st.row_off), _ptr(st.n_kp),
+                                            _ptr(pq), _ptr(pt), _ptr(out_off), P, _ptr(top2_idx), _ptr(top2_d2), self._stream()))
+        surv = self._empty((rows,), torch.uint8)
+        m_idx = self._empty((rows, 2), torch.int32)
+        m_pts = self._empty((rows, 4), torch.float32)
+        m_cnt = self._empty((P,), torch.int32)
+        n_filtered = self._empty((P,), torch.int32)
+        status = self._empty((P,), torch.int32)
+        self._check(self.lib.evz_filter_matches(self.h, _ptr(top2_idx), _ptr(top2_d2), _ptr(st.coords), _ptr(st.canon),
+                                                _ptr(st.row_off), _ptr(st.n_kp), _ptr(pq), _ptr(pt), _ptr(out_off), P,
+                                                st.max_kp, float(ratio), int(min_matching_pts),
+                                                _ptr(surv), _ptr(m_idx), _ptr(m_pts), _ptr(m_cnt), _ptr(n_filtered),
+                                                _ptr(status), self._stream()))
+        return PairResults(pair_q=pq, pair_t=pt, out_off=out_off, top2_idx=top2_idx, top2_d2=top2_d2, surv=surv,
+                           m_idx=m_idx, m_pts=m_pts, m_cnt=m_cnt, n_filtered=n_filtered, status=status)
+
+    # ------------------------------------------------------------------ K3 / K4
+    def find_homography(self, pts, off, cnt, status, max_cnt, n_hyp=1024, seed=0, pair_id_base=0, level=1,
+                        thresh=3.0, min_inlier_frac=0.0, fail_status=_lib.ST_NO_MODEL_1, pre_H=None):
+        """Batched seeded RANSAC + LM refit over the point lists pts[off[p]:off[p]+cnt[p]].
+        status is updated in place.  Returns dict(H, mask, inl_cnt, best_hyp, best_cnt, mask_best, H_best)."""
+        P = int(cnt.numel())
+        rows = int(pts.shape[0])
+        out = dict(H=torch.zeros((P, 9), dtype=torch.float64, device=self.device),
+                   mask=torch.zeros((rows,), dtype=torch.uint8, device=self.device),
+                   inl_cnt=torch.zeros((P,), dtype=torch.int32, device=self.device),
+                   best_hyp=torch.full((P,), -1, dtype=torch.int32, device=self.device),
+                   best_cnt=torch.zeros((P,), dtype=torch.int32, device=self.device),
+                   mask_best=torch.zeros((rows,), dtype=torch.uint8, device=self.device),
+                   H_best=torch.zeros((P, 9), dtype=torch.float64, device=self.device))
+        self._check(self.lib.evz_find_homography(self.h, _ptr(pts), _ptr(off), _ptr(cnt), P, int(max_cnt), _ptr(pre_H),
+                                                 int(n_hyp), int(seed) & 0xFFFFFFFF, int(pair_id_base), int(level),
+                                                 float(thresh), float(min_inlier_frac), int(fail_status),
+                                                 _ptr(status), _ptr(out["H"]), _ptr(out["mask"]), _ptr(out["inl_cnt"]),
+                                                 _ptr(out["best_hyp"]), _ptr(out["best_cnt"]), _ptr(out["mask_best"]),
+                                                 _ptr(out["H_best"]), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ K5
+    def static_filter(self, pts, off, cnt, H, status):
+        P = int(cnt.numel())
+        out_pts = self._empty(tuple(pts.shape), torch.float32)
+        out_cnt = self._empty((P,), torch.int32)
+        best_r = self._empty((P,), torch.int32)
+        flags = self._empty((P,), torch.int32)
+        self._check(self.lib.evz_static_filter(self.h, _ptr(pts), _ptr(off), _ptr(cnt), P, _ptr(H), _ptr(status),
+                                               _ptr(out_pts), _ptr(out_cnt), _ptr(best_r), _ptr(flags), self._stream()))
+        return out_pts, out_cnt, best_r, flags
+
+    # ------------------------------------------------------------------ whole per-pair path
+    def process_pairs(self, st: FrameStore, pair_q, pair_t, n_hyp=1024, seed=0, pair_id_base=0,
+                      ratio=0.5, thresh=3.0, min_matching_pts=4, pre_H=None) -> PairResults:
+        """match_static_kps + compute_homography for every pair (reference matching.py:131-163,
+        utils.py:328-363), all on the device."""
+        r = self.match(st, pair_q, pair_t, ratio, min_matching_pts)
+        mk = st.max_kp
+        h1 = self.find_homography(r.m_pts, r.out_off, r.m_cnt, r.status, mk, n_hyp, seed, pair_id_base, 1, thresh,
+                                  0.0, _lib.ST_NO_MODEL_1)
+        r.H1, r.mask1, r.mask1_best, r.best_hyp1, r.best_cnt1, r.inl1 = (h1["H"], h1["mask"], h1["mask_best"],
+                                                                      h1["best_hyp"], h1["best_cnt"], h1["inl_cnt"])
+        r.extra["H1_best"] = h1["H_best"]
+        r.static_pts, r.static_cnt, r.static_r, r.flags = self.static_filter(r.m_pts, r.out_off, r.m_cnt, r.H1, r.status)
+        h2 = self.find_homography(r.static_pts, r.out_off, r.static_cnt, r.status, mk, n_hyp, seed, pair_id_base, 2,
+                                  thresh, 0.7, _lib.ST_NO_MODEL_2, pre_H=pre_H)
+        r.H, r.mask2, r.mask2_best, r.best_hyp2, r.best_cnt2, r.inl2 = (h2["H"], h2["mask"], h2["mask_best"],
+                                                                     h2["best_hyp"], h2["best_cnt"], h2["inl_cnt"])
+        r.extra["H2_best"] = h2["H_best"]
+        return r
+
+    # ------------------------------------------------------------------ K6 / K7
+    def chain_scan(self, G, status, policy=True, seed_S=None, seed_G=None, want_fixed=True, want_summary=False,
+                   want_S=True):
+        """None-H fallback + cumulative superposition.  G: [P,9] or [P,3,3] f64 device tensor."""
+        G = G.reshape(-1, 9).contiguous()
+        P = G.shape[0]
+        S = self._empty((P, 9), torch.float64) if want_S else None
+        Hf = self._empty((P, 9), torch.float64) if (want_fixed and want_S) else None
+        summ = self._empty((20,), torch.float64) if want_summary else None
+        if P:
+            self._check(self.lib.evz_chain_scan(self.h, _ptr(G), _ptr(status), P, 1 if policy else 0, _ptr(seed_S), _ptr(seed_G),
+                                                _ptr(S), _ptr(Hf), _ptr(summ), self._stream()))
+        return S, Hf, summ
+
+    def remap(self, pts, frame_idx, S, sx, sy, inverse=False):
+        pts = pts.reshape(-1, 2).contiguous()
+        out = torch.empty_like(pts)
+        S = S.reshape(-1, 9).contiguous()
+        if pts.shape[0]:
+            self._check(self.lib.evz_remap(self.h, _ptr(pts), _ptr(frame_idx), pts.shape[0], _ptr(S), S.shape[0],
+                                           float(sx), float(sy), 1 if inverse else 0, _ptr(out), self._stream()))
+        return out
+
+    def max_movement(self, S, n_frames, height, width):
+        out = self._empty((1,), torch.float64)
+        S = S.reshape(-1, 9).contiguous()
+        self._check(self.lib.evz_max_movement(self.h, _ptr(S), int(n_frames), int(height), int(width), _ptr(out), self._stream()))
+        return out
+
+    # ------------------------------------------------------------------ video-level driver
+    def video_geometry(self, desc, coords, n_kp=None, n_hyp=1024, seed=0, none_h_processing=True,
+                       ratio=0.5, thresh=3.0, pair_id_base=0):
+        """Frame chain -> per-pair G, status, cumulative S and fixed-plane H (parallel formulation).
+        Host arrays in, host arrays out: this is the call bench.py times end to end."""
+        st = self.ingest(desc, coords, n_kp)
+        F = st.n_frames
+        pq = torch.arange(1, F, dtype=torch.int32)
+        pt = torch.arange(0, F - 1, dtype=torch.int32)
+        r = self.process_pairs(st, pq, pt, n_hyp, seed, pair_id_base, ratio, thresh)
+        S, Hf, _ = self.chain_scan(r.H, r.status, none_h_processing)
+        return dict(G=r.H.cpu().numpy().reshape(-1, 3, 3), status=r.status.cpu().numpy(),
+                    S=S.cpu().numpy().reshape(-1, 3, 3), H_fixed=Hf.cpu().numpy().reshape(-1, 3, 3), results=r, store=st)

@@ -1,0 +1,205 @@
+/*
+ * evz.h -- C ABI of libevz.so: the B200 (sm_100a) implementation of EvenVizion's
+ * frame-to-frame geometry hot path.
+ *
+ * The reference (gridl/EvenVizion) is pure Python and has no FFI of its own; the heavy
+ * arithmetic of this path lives behind two OpenCV call sites.  Each entry point below
+ * names the reference code it replaces (paths relative to the reference repo root).
+ * The Python shim in evenvizion_b200/ binds these with ctypes (see INTEGRATION.md for
+ * the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every pointer marked DEV is a CUDA device pointer owned by the caller; the
+ *     library owns only scratch inside the handle;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs
+ *     no host synchronisation except when scratch has to grow, and returns 0 on
+ *     success or a negative EVZ_E_* code (evz_last_error() has the text);
+ *   - per-pair outcomes are status codes in an output array (EVZ_ST_*), mirroring the
+ *     reference's NoMatchesException / HomographyException control flow;
+ *   - one handle per device, not thread-safe;
+ *   - there is no CPU fallback: without a CUDA device evz_create() fails.
+ *
+ * Frame store layout (built by evz_ingest)
+ *   A video is F frames; frame f has n_kp[f] keypoints stored in rows
+ *   [row_off[f], row_off[f] + n_kp[f]) of four parallel arrays.  row_off[f] is a
+ *   multiple of EVZ_ROW_ALIGN (256) and row_off[F] is the total row count, so every
+ *   256-row tensor-core tile belongs to exactly one frame; padding rows hold zero
+ *   descriptors and ckey = INT32_MAX.
+ *     desc   uint8  [rows][128]   descriptors, zero-padded to 128 bytes (ORB: 32 used)
+ *     ckey   int32  [rows]        (||d||^2 << 8) | (row & 255)
+ *     coords float  [rows][2]     keypoint (x, y)
+ *     canon  int32  [rows]        frame-local index of the first keypoint of the frame
+ *                                 with bit-identical (x, y)   (for remove_double_matching)
+ *   A frame pair p is (query frame pair_q[p] = the NEW frame = `self` in the reference,
+ *   train frame pair_t[p] = the PREVIOUS frame = `acceding`).  Per-pair variable-length
+ *   results start at row out_off[p] of the per-row output arrays and have capacity
+ *   n_kp[pair_q[p]]; for a video chain out_off[p] = row_off[pair_q[p]].
+ */
+#ifndef EVZ_H
+#define EVZ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EVZ_VERSION       100
+#define EVZ_ROW_ALIGN     256
+#define EVZ_DESC_BYTES    128
+#define EVZ_R_MAX         16383   /* largest displacement bin resolved exactly by evz_static_filter */
+#define EVZ_MAX_KP        12288   /* keypoints per frame supported by the shared-memory per-pair tables */
+
+/* error codes */
+#define EVZ_OK             0
+#define EVZ_E_CUDA        -1
+#define EVZ_E_ARG         -2
+#define EVZ_E_NOMEM       -3
+#define EVZ_E_NODEVICE    -4
+#define EVZ_E_UNSUPPORTED -5
+
+/* per-pair status (reference exception it mirrors) */
+#define EVZ_ST_OK           0
+#define EVZ_ST_FEW_MATCHES  1  /* NoMatchesException "len(matches) < min_matching_pts"   matching.py:113-116 */
+#define EVZ_ST_FEW_POINTS   3  /* < 4 points reach findHomography: cv2.error, uncaught in the reference     */
+#define EVZ_ST_NO_MODEL_1   4  /* NoMatchesException "can't find homography matrix"       matching.py:158-159 */
+#define EVZ_ST_NO_MODEL_2   5  /* HomographyException()                                    utils.py:361-362   */
+#define EVZ_ST_FEW_INLIERS  6  /* HomographyException "not enough points ..."              utils.py:359-360   */
+
+/* flags written by evz_static_filter into flags[p] */
+#define EVZ_FLAG_DISP_OVERFLOW 1 /* a displacement was non-finite or > EVZ_R_MAX (reference round() raises) */
+
+typedef struct evz_handle evz_handle;
+
+int         evz_version(void);
+int         evz_create(int device, evz_handle** out);
+void        evz_destroy(evz_handle* h);
+const char* evz_last_error(const evz_handle* h);     /* h may be NULL: last creation error */
+int         evz_sm_count(const evz_handle* h);
+
+/* ---- ingest: the step before the path.  Replaces the implicit
+ * np.float32 -> cv::Mat conversion inside knnMatch (matching.py:108) and prepares
+ * remove_double_matching's key comparison (utils.py:63-64).
+ *   raw_desc   DEV  [sum n_kp][d] of uint8 (raw_is_f32 = 0) or float (raw_is_f32 = 1),
+ *                   frames concatenated without padding; d <= 128
+ *   raw_coords DEV  float [sum n_kp][2]
+ *   raw_off    DEV  int64 [F+1]  first raw row of every frame
+ *   row_off    DEV  int32 [F+1]  first padded row of every frame (multiples of 256)
+ *   bad_count  DEV  int32 [1]    incremented for every descriptor value that is not an
+ *                                integer in [0,255] (float input; SURF cannot use this path)
+ */
+int evz_ingest(evz_handle* h, const void* raw_desc, int raw_is_f32, int d,
+               const float* raw_coords, const int64_t* raw_off, const int32_t* row_off, int n_frames,
+               uint8_t* desc, int32_t* ckey, float* coords, int32_t* canon, int32_t* bad_count,
+               void* stream);
+
+/* ---- K1: exact brute-force 2-NN.  Replaces
+ * cv2.DescriptorMatcher_create("BruteForce").knnMatch(q, t, 2) at matching.py:102-108.
+ * u8 x u8 -> s32 tcgen05.mma (kind::i8), TMA-staged tiles, TMEM accumulators, fused
+ * ||a||^2 + ||b||^2 - 2ab / top-2 epilogue.  Ties resolve to the lowest train index.
+ *   top2_idx DEV int32 [rows][2]  train keypoint index (frame-local), -1 when absent
+ *   top2_d2  DEV int32 [rows][2]  exact squared L2 distance,          -1 when absent
+ * (knnMatch's DMatch.distance is sqrtf((float)d2), bit for bit.)
+ */
+int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t* ckey, int64_t total_rows,
+                   const int32_t* row_off, const int32_t* n_kp,
+                   const int32_t* pair_q, const int32_t* pair_t, const int32_t* out_off, int n_pairs,
+                   int32_t* top2_idx, int32_t* top2_d2, void* stream);
+
+/* ---- K1b/K2: Lowe ratio test + many-to-one filter + coordinate de-dup + gather.  Replaces
+ * lowes_ratio_test / filter_corresponding_points (matching.py:166-239), the point gather
+ * (matching.py:117-118) and remove_double_matching (utils.py:41-68).
+ *   max_kp   upper bound of n_kp over the frames involved (sizes shared memory; <= EVZ_MAX_KP)
+ *   surv     DEV uint8  [rows]     1 where the query passes the ratio test (may be NULL)
+ *   m_idx    DEV int32  [rows][2]  (query, train) of the de-duplicated matches, in order
+ *   m_pts    DEV float  [rows][4]  (ax, ay, bx, by): a = query/self, b = train/acceding
+ *   m_cnt    DEV int32  [P]        number of matches after de-dup
+ *   n_filtered DEV int32 [P]       len(matches) before de-dup (what min_matching_pts tests)
+ *   status   DEV int32  [P]        EVZ_ST_OK or EVZ_ST_FEW_MATCHES
+ */
+int evz_filter_matches(evz_handle* h, const int32_t* top2_idx, const int32_t* top2_d2,
+                       const float* coords, const int32_t* canon,
+                       const int32_t* row_off, const int32_t* n_kp,
+                       const int32_t* pair_q, const int32_t* pair_t, const int32_t* out_off, int n_pairs,
+                       int max_kp, double ratio, int min_matching_pts,
+                       uint8_t* surv, int32_t* m_idx, float* m_pts, int32_t* m_cnt,
+                       int32_t* n_filtered, int32_t* status, void* stream);
+
+/* ---- K3 + K4: seeded RANSAC homography + refit.  Replaces
+ * cv2.findHomography(a, b, cv2.RANSAC, thresh) at matching.py:156-157 (level 1) and
+ * utils.py:356-358 (level 2), including the 70 % inlier gate of utils.py:359-360 when
+ * min_inlier_frac > 0.  Pairs whose status is non-zero on entry are skipped.
+ *   pts        DEV float [rows][4]  point pairs of pair p at rows [off[p], off[p]+cnt[p])
+ *   max_cnt    upper bound of cnt[p] (sizes shared memory; <= EVZ_MAX_KP)
+ *   pre_H      DEV double [P][9] or NULL: both point sets are first mapped through this
+ *              matrix in f64 and rounded to f32 (utils.py:351-355, matrix_H_prev)
+ *   n_hyp      hypotheses per pair (counter-based sampler: seed, pair_id_base + p, level)
+ *   fail_status value written to status[p] when no model is found (EVZ_ST_NO_MODEL_1/2)
+ * outputs (any may be NULL except H and status)
+ *   H          DEV double [P][9]  refined homography (normalised DLT + LM), h22 = 1
+ *   mask       DEV uint8 [rows]   final inlier mask: f32 reprojection error of H <= thresh^2
+ *   inl_cnt    DEV int32 [P]      sum(mask)
+ *   best_hyp   DEV int32 [P]      winning hypothesis (max inliers, ties -> lowest index)
+ *   best_cnt   DEV int32 [P]      its inlier count
+ *   mask_best  DEV uint8 [rows]   its inlier mask (the refit set)
+ *   H_best     DEV double [P][9]  its 4-point model
+ */
+int evz_find_homography(evz_handle* h, const float* pts, const int32_t* off, const int32_t* cnt, int n_pairs,
+                        int max_cnt, const double* pre_H, int n_hyp, uint32_t seed, int64_t pair_id_base, int level,
+                        double thresh, double min_inlier_frac, int fail_status,
+                        int32_t* status, double* H, uint8_t* mask, int32_t* inl_cnt,
+                        int32_t* best_hyp, int32_t* best_cnt, uint8_t* mask_best, double* H_best,
+                        void* stream);
+
+/* ---- K5: displacement-mode static-point filter.  Replaces find_point_displacement
+ * (utils.py:289-325) + get_largest_group_points (utils.py:258-286).
+ *   out_pts DEV float [rows][4] kept point pairs (order preserved), out_cnt DEV int32 [P],
+ *   best_r  DEV int32 [P] the winning rounded displacement, flags DEV int32 [P] (EVZ_FLAG_*)
+ */
+int evz_static_filter(evz_handle* h, const float* pts, const int32_t* off, const int32_t* cnt, int n_pairs,
+                      const double* H, const int32_t* status,
+                      float* out_pts, int32_t* out_cnt, int32_t* best_r, int32_t* flags, void* stream);
+
+/* ---- K6: None-H fallback + cumulative superposition as a parallel prefix product.
+ * Replaces video_processing.py:94-103 and matrix_superposition / superposition_dict
+ * (utils.py:118-145, 184-211).
+ *   G       DEV double [P][9]  frame-plane step matrices (new frame -> previous frame)
+ *   status  DEV int32  [P]     non-zero = "H is None"
+ *   policy  1 = none_H_processing=True (reuse the previous pair's matrix), 0 = identity step
+ *   seed_S  DEV double [9] or NULL  superposition before the first pair (identity if NULL)
+ *   seed_G  DEV double [9] or NULL  last valid step matrix before the first pair
+ * outputs
+ *   S       DEV double [P][9]  S_k = normalise(S_{k-1} . Gfilled_k): frame k+1 -> fixed plane
+ *   H_fixed DEV double [P][9]  S_k . S_{k-1}^-1 normalised: what the reference stores in
+ *                              dict_with_homography_matrix.json (may be NULL)
+ *   summary DEV double [20]    shard summary for the cross-GPU all-gather (may be NULL):
+ *             [0..8]  R = product of the steps from the first valid pair on (filled)
+ *             [9..17] last valid G of the shard, [18] number of leading invalid pairs,
+ *             [19] 1 if the shard has a valid pair
+ */
+int evz_chain_scan(evz_handle* h, const double* G, const int32_t* status, int n_pairs, int policy,
+                   const double* seed_S, const double* seed_G,
+                   double* S, double* H_fixed, double* summary, void* stream);
+
+/* ---- K7: object-coordinate remap.  Replaces from_original_to_fix / from_fix_to_original
+ * (fixed_coordinate_system.py:19-122): (x', y') = around(T . (sx*x, sy*y, 1), 2) with
+ * T = S[frame] (inverse = 0) or S[frame]^-1 (inverse = 1).
+ *   pts_in DEV double [n][2], frame_idx DEV int32 [n] (row of S), S DEV double [F][9]
+ */
+int evz_remap(evz_handle* h, const double* pts_in, const int32_t* frame_idx, int64_t n,
+              const double* S, int n_frames, double sx, double sy, int inverse,
+              double* pts_out, void* stream);
+
+/* ---- dense remap + max-movement metric.  Replaces the per-pixel
+ * np.apply_along_axis(homography_transformation, ...) of heatmap_video_processing
+ * (visualization/processing_visualization.py:404-418): max over the first n_frames rows of S
+ * and all pixels of the w x h grid of max(x', y').
+ *   out_max DEV double [1]
+ */
+int evz_max_movement(evz_handle* h, const double* S, int n_frames, int height, int width,
+                     double* out_max, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVZ_H */

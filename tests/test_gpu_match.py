@@ -1,0 +1,149 @@
+"""K1 / K1b / K2 parity: CUDA path (through the C ABI) vs the oracle.  Needs a B200."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import matching
+
+pytestmark = pytest.mark.gpu
+
+
+def _ragged_frames(counts, d=128, seed=0, dup_coords=False):
+    rng = np.random.default_rng(seed)
+    frames = []
+    base = rng.integers(0, 256, (max(counts) + 8, d)).astype(np.uint8)
+    for i, n in enumerate(counts):
+        desc = rng.integers(0, 120, (n, d)).astype(np.uint8)
+        k = min(n, len(base)) * 2 // 3                      # shared structure so that the ratio test has survivors
+        if k:
+            sel = rng.permutation(len(base))[:k]
+            desc[:k] = np.clip(base[sel].astype(np.int32) + rng.integers(-3, 4, (k, d)), 0, 255).astype(np.uint8)
+        coords = (rng.random((n, 2)) * [400, 224]).astype(np.float32)
+        if dup_coords and n > 30:
+            coords[10:20] = coords[0:10]
+            coords[25] = coords[3]
+        frames.append((coords, desc))
+    return frames
+
+
+def _ingest(engine, frames):
+    desc = np.concatenate([f[1] for f in frames]) if frames else np.zeros((0, 128), np.uint8)
+    coords = np.concatenate([f[0] for f in frames])
+    return engine.ingest(desc, coords, [len(f[1]) for f in frames])
+
+
+def _check_pair(engine, st, r, p, frames, qf, tf):
+    o = int(st.row_off_h[qf])
+    nq = len(frames[qf][1])
+    idx, d2 = matching.knn_top2(frames[qf][1], frames[tf][1])
+    g_idx = r.top2_idx[o:o + nq].cpu().numpy()
+    g_d2 = r.top2_d2[o:o + nq].cpu().numpy().astype(np.int64)
+    assert np.array_equal(g_idx, idx), f"pair {p}: top-2 indices differ"
+    assert np.array_equal(g_d2, d2), f"pair {p}: squared distances differ"
+    surv = matching.ratio_survivors(idx, d2)
+    assert np.array_equal(r.surv[o:o + nq].cpu().numpy().astype(bool), surv), f"pair {p}: ratio survivors differ"
+    mk = matching.match_kps(frames[qf][0], frames[qf][1], frames[tf][0], frames[tf][1])
+    assert int(r.n_filtered[p]) == len(mk["matches"])
+    assert int(r.status[p]) == mk["status"]
+    m = int(r.m_cnt[p])
+    assert m == len(mk["pts_a"])
+    if m:
+        pts = r.m_pts[o:o + m].cpu().numpy()
+        assert np.array_equal(pts[:, :2], mk["pts_a"]) and np.array_equal(pts[:, 2:], mk["pts_b"])
+        gi = r.m_idx[o:o + m].cpu().numpy()
+        assert np.array_equal(gi[:, 0], mk["matches"][mk["keep"], 1])
+        assert np.array_equal(gi[:, 1], mk["matches"][mk["val"], 0])
+
+
+def test_ingest_layout(engine):
+    frames = _ragged_frames([300, 1, 257, 0, 512], seed=3, dup_coords=True)
+    st = _ingest(engine, frames)
+    assert st.rows % 256 == 0 and (st.row_off_h % 256 == 0).all()
+    desc = st.desc.cpu().numpy(); ckey = st.ckey.cpu().numpy(); canon = st.canon.cpu().numpy(); co = st.coords.cpu().numpy()
+    for f, (c, d) in enumerate(frames):
+        o = st.row_off_h[f]; n = len(d); e = st.row_off_h[f + 1]
+        assert np.array_equal(desc[o:o + n], d)
+        assert (desc[o + n:e] == 0).all() and (ckey[o + n:e] == 2 ** 31 - 1).all()
+        norm = (d.astype(np.int64) ** 2).sum(1)
+        assert np.array_equal(ckey[o:o + n], (norm << 8) | (np.arange(o, o + n) & 255))
+        assert np.array_equal(co[o:o + n], c)
+        first = {}
+        exp = np.array([first.setdefault((float(x), float(y)), i) for i, (x, y) in enumerate(c)], np.int32).reshape(-1)
+        assert np.array_equal(canon[o:o + n], exp)
+
+
+def test_match_ragged_pairs(engine):
+    counts = [300, 333, 257, 1, 0, 600, 128, 129]
+    frames = _ragged_frames(counts, seed=1, dup_coords=True)
+    st = _ingest(engine, frames)
+    pq = list(range(1, len(counts)))
+    pt = list(range(0, len(counts) - 1))
+    r = engine.match(st, pq, pt)
+    torch.cuda.synchronize()
+    for p, (qf, tf) in enumerate(zip(pq, pt)):
+        _check_pair(engine, st, r, p, frames, qf, tf)
+
+
+def test_match_golden_sets(engine, golden):
+    for i in range(int(golden["knn_n"])):
+        q, t = golden[f"knn{i}_q"], golden[f"knn{i}_t"]
+        frames = [(np.zeros((len(t), 2), np.float32) + np.arange(len(t))[:, None].astype(np.float32), t),
+                  (np.zeros((len(q), 2), np.float32) + np.arange(len(q))[:, None].astype(np.float32), q)]
+        if q.shape[1] != t.shape[1]:
+            continue
+        st = _ingest(engine, frames)
+        r = engine.match(st, [1], [0])
+        nq = len(q)
+        idx = r.top2_idx[st.row_off_h[1]:st.row_off_h[1] + nq].cpu().numpy()
+        d2 = r.top2_d2[st.row_off_h[1]:st.row_off_h[1] + nq].cpu().numpy()
+        assert np.array_equal(idx, golden[f"knn{i}_idx"]), i
+        dist = np.where(idx >= 0, np.sqrt(np.maximum(d2, 0).astype(np.float32)), np.float32(-1))
+        assert np.array_equal(dist, golden[f"knn{i}_dist"]), i      # == cv2 DMatch.distance bit for bit
+        m = int(r.n_filtered[0])
+        assert m == len(golden[f"knn{i}_lowe"]), i
+
+
+def test_match_reference_pairs(engine, golden):
+    """match_kps outputs of the reference itself (synthetic pairs and the bundled clip)."""
+    for i in range(int(golden["mk_n"])):
+        frames = [(golden[f"mk{i}_tc"], golden[f"mk{i}_td"]), (golden[f"mk{i}_qc"], golden[f"mk{i}_qd"])]
+        st = _ingest(engine, frames)
+        r = engine.match(st, [1], [0])
+        m = int(r.m_cnt[0]); o = int(st.row_off_h[1])
+        pts = r.m_pts[o:o + m].cpu().numpy()
+        assert np.array_equal(pts[:, :2], golden[f"mk{i}_pts_a"]) and np.array_equal(pts[:, 2:], golden[f"mk{i}_pts_b"])
+    n = int(golden["clip_n"])
+    frames = [(golden[f"clip{f}_c"], golden[f"clip{f}_d"]) for f in range(n)]
+    st = _ingest(engine, frames)
+    r = engine.match(st, list(range(1, n)), list(range(0, n - 1)))
+    for p in range(n - 1):
+        m = int(r.m_cnt[p]); o = int(st.row_off_h[p + 1])
+        pts = r.m_pts[o:o + m].cpu().numpy()
+        assert np.array_equal(pts[:, :2], golden[f"clip{p}_pts_a"]), p
+        assert np.array_equal(pts[:, 2:], golden[f"clip{p}_pts_b"]), p
+
+
+def test_match_full_size_properties(engine):
+    """BASELINE shape (2048 kp/frame): exactness against an independent on-device computation
+    (f32 GEMM of u8 values is exact below 2^24) and size-independent properties."""
+    from evenvizion_b200 import synth
+    ch = synth.make_chain(9, 2048, seed=5, device="cuda")
+    st = engine.ingest(ch["desc"], ch["coords"])
+    r = engine.match(st, list(range(1, 9)), list(range(0, 8)))
+    d = ch["desc"].float()
+    for p in range(8):
+        q, t = d[p + 1], d[p]
+        d2 = (q * q).sum(1)[:, None] + (t * t).sum(1)[None, :] - 2 * (q @ t.T)
+        key = d2.double() * 4096 + torch.arange(2048, device="cuda", dtype=torch.float64)[None, :]
+        top = torch.topk(key, 2, dim=1, largest=False).values
+        idx = (top % 4096).long(); val = torch.div(top, 4096, rounding_mode="floor").long()
+        o = int(st.row_off_h[p + 1])
+        assert torch.equal(r.top2_idx[o:o + 2048].long(), idx)
+        assert torch.equal(r.top2_d2[o:o + 2048].long(), val)
+    # idempotence / determinism: a second run is bit-identical
+    r2 = engine.match(st, list(range(1, 9)), list(range(0, 8)))
+    assert torch.equal(r.top2_idx, r2.top2_idx) and torch.equal(r.top2_d2, r2.top2_d2)
+    # self-match: every descriptor's nearest neighbour in its own frame is at distance 0
+    rs = engine.match(st, [3], [3])
+    o = int(st.row_off_h[3])
+    assert (rs.top2_d2[o:o + 2048, 0] == 0).all()

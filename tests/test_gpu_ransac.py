@@ -1,0 +1,130 @@
+"""K3 / K4 / K5 parity: seeded RANSAC, refit, static filter vs the oracle.  Needs a B200."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ransac, static_filter
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(rng, n, out_frac, noise=0.5):
+    a = (rng.random((n, 2)) * [1920, 1080]).astype(np.float32)
+    th = rng.normal() * 0.01
+    s = 1 + rng.normal() * 0.01
+    Ht = np.array([[s * np.cos(th), -s * np.sin(th), rng.normal() * 8], [s * np.sin(th), s * np.cos(th), rng.normal() * 8],
+                   [rng.normal() * 1e-5, rng.normal() * 1e-5, 1]])
+    p = np.c_[a, np.ones(n)] @ Ht.T
+    b = (p[:, :2] / p[:, 2:] + rng.normal(size=(n, 2)) * noise).astype(np.float32)
+    o = rng.random(n) < out_frac
+    b[o] = (rng.random((int(o.sum()), 2)) * [1920, 1080]).astype(np.float32)
+    return a, b
+
+
+def _pack(sets, dev):
+    cnt = np.array([len(a) for a, _ in sets], np.int32)
+    cap = (cnt + 3) // 4 * 4 + 4
+    off = np.zeros(len(sets), np.int32)
+    off[1:] = np.cumsum(cap)[:-1]
+    pts = np.zeros((int(cap.sum()), 4), np.float32)
+    for i, (a, b) in enumerate(sets):
+        pts[off[i]:off[i] + cnt[i], :2] = a
+        pts[off[i]:off[i] + cnt[i], 2:] = b
+    return (torch.from_numpy(pts).to(dev), torch.from_numpy(off).to(dev), torch.from_numpy(cnt).to(dev), off, cnt)
+
+
+def _px(H, a):
+    p = np.c_[a.astype(np.float64), np.ones(len(a))] @ np.asarray(H, np.float64).reshape(3, 3).T
+    return p[:, :2] / p[:, 2:]
+
+
+def test_find_homography_vs_oracle(engine):
+    rng = np.random.default_rng(11)
+    sets = [_mk(rng, n, f) for n, f in [(1200, 0.2), (700, 0.5), (300, 0.0), (64, 0.3), (5, 0.0), (4, 0.0), (3, 0.0),
+                                         (2000, 0.8), (9, 0.4)]]
+    pts, off, cnt, off_h, cnt_h = _pack(sets, engine.device)
+    status = torch.zeros(len(sets), dtype=torch.int32, device=engine.device)
+    n_hyp, seed, base, level = 1024, 7, 100, 1
+    out = engine.find_homography(pts, off, cnt, status, int(cnt_h.max()), n_hyp, seed, base, level, 3.0, 0.0, 4)
+    torch.cuda.synchronize()
+    st = status.cpu().numpy()
+    for i, (a, b) in enumerate(sets):
+        ref = ransac.find_homography_seeded(a, b, n_hyp, seed, base + i, level, 3.0)
+        assert st[i] == ref["status"], (i, st[i], ref["status"])
+        if ref["status"] != 0:
+            continue
+        o, m = off_h[i], cnt_h[i]
+        if ref["hyp"] is not None:
+            assert int(out["best_hyp"][i]) == ref["hyp"]["best"], i                       # same winning hypothesis
+            assert int(out["best_cnt"][i]) == ref["hyp"]["best_count"], i
+            Hb = out["H_best"][i].cpu().numpy()
+            assert np.array_equal(Hb, ref["hyp"]["H_all"][ref["hyp"]["best"]]), i         # bit-exact f64 4-point solve
+        mb = out["mask_best"][o:o + m].cpu().numpy().astype(bool)
+        assert np.array_equal(mb, ref["mask_best"]), i                                    # criterion (b): bit-exact masks
+        H = out["H"][i].cpu().numpy()
+        inl = ref["mask_best"]
+        err = np.linalg.norm(_px(H, a[inl]) - _px(ref["H"], a[inl]), axis=1).mean()
+        assert err < 1e-3, (i, err)                                                       # criterion (c)
+        # final mask: identical except where the f32 error sits on the threshold
+        gm = out["mask"][o:o + m].cpu().numpy()
+        e = ransac.reproj_err32(ref["H"].ravel(), a, b)
+        diff = gm != ref["mask"]
+        assert (np.abs(e[diff] - 9.0) < 1e-2).all(), i
+        assert int(out["inl_cnt"][i]) == int(gm.sum())
+
+
+def test_find_homography_against_opencv_refit(engine):
+    """criterion (c) against live OpenCV: cv2.findHomography(pts[mask_best], method 0)."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(12)
+    sets = [_mk(rng, n, f) for n, f in [(1500, 0.3), (400, 0.1), (90, 0.5)]]
+    pts, off, cnt, off_h, cnt_h = _pack(sets, engine.device)
+    status = torch.zeros(len(sets), dtype=torch.int32, device=engine.device)
+    out = engine.find_homography(pts, off, cnt, status, int(cnt_h.max()), 1024, 1, 0, 1)
+    for i, (a, b) in enumerate(sets):
+        o, m = off_h[i], cnt_h[i]
+        mb = out["mask_best"][o:o + m].cpu().numpy().astype(bool)
+        Hcv, _ = cv2.findHomography(a[mb], b[mb], 0)
+        err = np.linalg.norm(_px(out["H"][i].cpu().numpy(), a[mb]) - _px(Hcv, a[mb]), axis=1).mean()
+        assert err < 1e-3, (i, err)
+
+
+def test_pre_transform_and_gate(engine):
+    rng = np.random.default_rng(13)
+    a, b = _mk(rng, 500, 0.5)
+    T = np.array([[1.01, 0.02, 5.0], [-0.01, 0.99, -3.0], [1e-5, -2e-5, 1.0]])
+    pts, off, cnt, off_h, cnt_h = _pack([(a, b)], engine.device)
+    status = torch.zeros(1, dtype=torch.int32, device=engine.device)
+    pre = torch.from_numpy(T.reshape(1, 9)).to(engine.device)
+    out = engine.find_homography(pts, off, cnt, status, 500, 512, 3, 5, 2, 3.0, 0.7, 5, pre_H=pre)
+    def tr(p):
+        q = np.c_[p.astype(np.float64), np.ones(len(p))]
+        X = (T[0, 0] * q[:, 0] + T[0, 1] * q[:, 1]) + T[0, 2]
+        Y = (T[1, 0] * q[:, 0] + T[1, 1] * q[:, 1]) + T[1, 2]
+        W = (T[2, 0] * q[:, 0] + T[2, 1] * q[:, 1]) + T[2, 2]
+        return np.stack([X / W, Y / W], 1).astype(np.float32)
+    ref = ransac.find_homography_seeded(tr(a), tr(b), 512, 3, 5, 2, 3.0)
+    assert np.array_equal(out["mask_best"][:500].cpu().numpy().astype(bool), ref["mask_best"])
+    assert int(status[0]) == 6          # ~50 % inliers < 70 % -> HomographyException
+
+
+def test_static_filter_vs_oracle(engine, golden):
+    sets, Hs = [], []
+    for i in range(int(golden["fh_n"])):
+        sets.append((golden[f"fh{i}_a"], golden[f"fh{i}_b2"]))
+        Hs.append(golden[f"fh{i}_Hr"].ravel())
+    rng = np.random.default_rng(5)
+    a, b = _mk(rng, 800, 0.3, noise=2.0)
+    sets.append((a, b)); Hs.append(np.eye(3).ravel())
+    pts, off, cnt, off_h, cnt_h = _pack(sets, engine.device)
+    status = torch.zeros(len(sets), dtype=torch.int32, device=engine.device)
+    H = torch.from_numpy(np.array(Hs)).to(engine.device)
+    out_pts, out_cnt, best_r, flags = engine.static_filter(pts, off, cnt, H, status)
+    for i, (a, b) in enumerate(sets):
+        keep, br, bad = static_filter.static_points(Hs[i], a, b)
+        assert int(best_r[i]) == br and int(out_cnt[i]) == len(keep) and bool(int(flags[i])) == bad
+        g = out_pts[off_h[i]:off_h[i] + len(keep)].cpu().numpy()
+        assert np.array_equal(g[:, :2], a[keep]) and np.array_equal(g[:, 2:], b[keep])
+    for i in range(int(golden["fh_n"])):      # and against the reference's own output
+        g = out_pts[off_h[i]:off_h[i] + int(out_cnt[i])].cpu().numpy()
+        assert np.array_equal(g[:, :2], golden[f"fh{i}_static_a"]) and np.array_equal(g[:, 2:], golden[f"fh{i}_static_b"])

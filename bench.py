@@ -48,9 +48,9 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks / throttle reasons; started before warm-up, samples filtered to the timed window."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
@@ -58,8 +58,8 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -69,29 +69,37 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, t_begin, t_end):
+        """t_begin / t_end: time.time() around the timed region."""
+        import datetime
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, sm_all, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                c, m = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+            sm_all.append(c); mx.append(m)
+            if t_begin - 0.02 <= ts <= t_end + 0.02:
+                sm.append(c)
+                for n, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        use = sm if sm else sm_all[-5:]
+        return dict(sm_mhz=float(np.median(use)) if use else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm), samples_total=len(sm_all))
 
 
 def cpu_reference_run(frames, cores, steps, warmup):
@@ -212,13 +220,14 @@ def run_ours(args, cfg):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        r, S, _ = step(False)
-    sync_all()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        r, S, _ = step(False)
+    sync_all()
     t0, t1 = ev(), ev()
+    w_begin = time.time()
     evs = []
     t0.record()
     for _ in range(args.steps):
@@ -226,7 +235,8 @@ def run_ours(args, cfg):
         evs.append(e)
     t1.record()
     sync_all()
-    clocks = sampler.stop() if rank == 0 else None
+    w_end = time.time()
+    clocks = sampler.stop(w_begin, w_end) if rank == 0 else None
     total_ms = t0.elapsed_time(t1)
     for e in evs:
         match_ms.append(e[0].elapsed_time(e[1])); ransac_ms.append(e[1].elapsed_time(e[2]))

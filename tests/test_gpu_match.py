@@ -142,7 +142,8 @@ def test_match_full_size_properties(engine):
         assert torch.equal(r.top2_d2[o:o + 2048].long(), val)
     # idempotence / determinism: a second run is bit-identical
     r2 = engine.match(st, list(range(1, 9)), list(range(0, 8)))
-    assert torch.equal(r.top2_idx, r2.top2_idx) and torch.equal(r.top2_d2, r2.top2_d2)
+    q0 = int(st.row_off_h[1])            # rows of frame 0 are never a query: not written
+    assert torch.equal(r.top2_idx[q0:], r2.top2_idx[q0:]) and torch.equal(r.top2_d2[q0:], r2.top2_d2[q0:])
     # self-match: every descriptor's nearest neighbour in its own frame is at distance 0
     rs = engine.match(st, [3], [3])
     o = int(st.row_off_h[3])

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256)
 static_filter_kernel(const float* __restrict__ pts, const int32_t* __restrict__ off, const int32_t* __restrict__ cnt,
                      const double* __restrict__ Hs, const int32_t* __restrict__ status,
                      float* __restrict__ out_pts, int32_t* __restrict__ out_cnt, int32_t* __restrict__ best_r,
-                     int32_t* __restrict__ flags) {
+                     int32_t* __restrict__ flags, int32_t* __restrict__ r_out) {
     extern __shared__ __align__(16) uint8_t sf_smem[];
     uint32_t* hist = reinterpret_cast<uint32_t*>(sf_smem);
     int32_t* first = reinterpret_cast<int32_t*>(sf_smem + ((kBins + 1) / 2) * 4);
@@ -49,6 +49,7 @@ static_filter_kernel(const float* __restrict__ pts, const int32_t* __restrict__ 
     const float4* P = reinterpret_cast<const float4*>(pts) + o;
     for (int i = tid; i < m; i += blockDim.x) {
         const int r = disp_bin(H, P[i]);
+        if (r_out) r_out[o + i] = r;
         atomicAdd(&hist[r >> 1], 1u << (16 * (r & 1)));
         atomicMin(&first[r], i);
         if (r > EVZ_R_MAX) s_over = 1;
@@ -306,7 +307,8 @@ __global__ void max_reduce_kernel(const double* __restrict__ partial, int n, dou
 
 extern "C" int evz_static_filter(evz_handle* h, const float* pts, const int32_t* off, const int32_t* cnt, int n_pairs,
                                  const double* H, const int32_t* status,
-                                 float* out_pts, int32_t* out_cnt, int32_t* best_r, int32_t* flags, void* stream) {
+                                 float* out_pts, int32_t* out_cnt, int32_t* best_r, int32_t* flags, int32_t* r_out,
+                                 void* stream) {
     if (!h) return EVZ_E_ARG;
     EVZ_REQUIRE(h, pts && off && cnt && H && status && out_pts && out_cnt && best_r && flags, "null pointer");
     if (n_pairs <= 0) return EVZ_OK;
@@ -316,7 +318,7 @@ extern "C" int evz_static_filter(evz_handle* h, const float* pts, const int32_t*
         EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::static_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
-    evz::static_filter_kernel<<<n_pairs, 256, smem, static_cast<cudaStream_t>(stream)>>>(pts, off, cnt, H, status, out_pts, out_cnt, best_r, flags);
+    evz::static_filter_kernel<<<n_pairs, 256, smem, static_cast<cudaStream_t>(stream)>>>(pts, off, cnt, H, status, out_pts, out_cnt, best_r, flags, r_out);
     EVZ_LAUNCH_CHECK(h);
     return EVZ_OK;
 }

@@ -227,14 +227,18 @@ class GeometryEngine:
         return out
 
     # ------------------------------------------------------------------ K5
-    def static_filter(self, pts, off, cnt, H, status):
+    def static_filter(self, pts, off, cnt, H, status, want_r=False):
         P = int(cnt.numel())
+        r_out = self._empty((int(pts.shape[0]),), torch.int32) if want_r else None
         out_pts = self._empty(tuple(pts.shape), torch.float32)
         out_cnt = self._empty((P,), torch.int32)
         best_r = self._empty((P,), torch.int32)
         flags = self._empty((P,), torch.int32)
         self._check(self.lib.evz_static_filter(self.h, _ptr(pts), _ptr(off), _ptr(cnt), P, _ptr(H), _ptr(status),
-                                               _ptr(out_pts), _ptr(out_cnt), _ptr(best_r), _ptr(flags), self._stream()))
+                                               _ptr(out_pts), _ptr(out_cnt), _ptr(best_r), _ptr(flags), _ptr(r_out),
+                                               self._stream()))
+        if want_r:
+            return out_pts, out_cnt, best_r, flags, r_out
         return out_pts, out_cnt, best_r, flags
 
     # ------------------------------------------------------------------ whole per-pair path

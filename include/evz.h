@@ -155,10 +155,12 @@ int evz_find_homography(evz_handle* h, const float* pts, const int32_t* off, con
  * (utils.py:289-325) + get_largest_group_points (utils.py:258-286).
  *   out_pts DEV float [rows][4] kept point pairs (order preserved), out_cnt DEV int32 [P],
  *   best_r  DEV int32 [P] the winning rounded displacement, flags DEV int32 [P] (EVZ_FLAG_*)
+ *   r_out   DEV int32 [rows] or NULL: round(||H a - b||) of every point (find_point_displacement's key)
  */
 int evz_static_filter(evz_handle* h, const float* pts, const int32_t* off, const int32_t* cnt, int n_pairs,
                       const double* H, const int32_t* status,
-                      float* out_pts, int32_t* out_cnt, int32_t* best_r, int32_t* flags, void* stream);
+                      float* out_pts, int32_t* out_cnt, int32_t* best_r, int32_t* flags, int32_t* r_out,
+                      void* stream);
 
 /* ---- K6: None-H fallback + cumulative superposition as a parallel prefix product.
  * Replaces video_processing.py:94-103 and matrix_superposition / superposition_dict

@@ -1,0 +1,151 @@
+"""CPU-only tests: the C ABI library loads and exports what include/evz.h declares, the product
+fails loudly without a GPU, and the host logic of the multi-GPU path (gloo, world size 2)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import evenvizion_b200
+from evenvizion_b200 import _lib
+from evenvizion_b200.distributed import shard_range, seeds_from_summaries
+from evenvizion_b200.engine import GeometryEngine
+from oracle import chain
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "evz.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(evz_\w+)\s*\(([^;{]*?)\)\s*;", text):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_library_exports_every_declared_symbol():
+    decl = _declared()
+    assert len(decl) >= 13
+    lib = _lib.load()
+    for name, nargs in decl.items():
+        assert hasattr(lib, name), f"{name} declared in evz.h but not exported by libevz.so"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+        assert len(_lib.SIGNATURES[name]) == nargs, f"{name}: evz.h has {nargs} parameters, ctypes binding {len(_lib.SIGNATURES[name])}"
+    assert lib.evz_version() == 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    assert lib.evz_create(0, ctypes.byref(h)) == -4            # EVZ_E_NODEVICE
+    assert b"no CPU fallback" in lib.evz_last_error(None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        GeometryEngine(0)
+    import evenvizion_b200.processing as p
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        p.KeyPoints(np.zeros((5, 2), np.float32), np.zeros((5, 128), np.uint8)).match_kps(
+            p.KeyPoints(np.zeros((5, 2), np.float32), np.zeros((5, 128), np.uint8)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        p.superposition_dict({2: {"H": np.eye(3).tolist()}})
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "evenvizion_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_layout_and_shards():
+    ro = GeometryEngine.layout([300, 1, 0, 256, 257])
+    assert ro.tolist() == [0, 512, 768, 1024, 1280, 1792]
+    for n, w in [(10, 4), (100000, 8), (3, 8), (0, 2)]:
+        r = [shard_range(n, k, w) for k in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+        assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def _summary(G, valid, policy):
+    """Host restatement of the evz_chain_scan shard summary (include/evz.h) via the oracle."""
+    n = len(G)
+    idx = np.nonzero(valid)[0]
+    s = np.zeros(20)
+    if len(idx) == 0:
+        s[0:9] = np.eye(3).ravel(); s[9:18] = np.eye(3).ravel(); s[18] = n; s[19] = 0
+        return s
+    lead = int(idx[0])
+    Gf = chain.fill_none(G[lead:], valid[lead:], policy)
+    s[0:9] = chain.chain_products(Gf)[-1].ravel()
+    s[9:18] = G[idx[-1]].ravel(); s[18] = lead; s[19] = 1
+    return s
+
+
+def _rand_chain(P, seed):
+    rng = np.random.default_rng(seed)
+    G = np.tile(np.eye(3), (P, 1, 1))
+    G[:, :2, :] += rng.normal(size=(P, 2, 3)) * [0.002, 0.002, 2.0]
+    valid = rng.random(P) > 0.15
+    valid[:2] = False
+    valid[P // 2 - 3:P // 2 + 4] = False          # failures straddling the shard boundary
+    return G, valid
+
+
+@pytest.mark.parametrize("policy", [True, False])
+def test_seeds_from_summaries_match_global_chain(policy):
+    G, valid = _rand_chain(240, 1)
+    ref = chain.chain_products(chain.fill_none(G, valid, policy))
+    world = 5
+    sums = [_summary(G[a:b], valid[a:b], policy) for a, b in (shard_range(240, r, world) for r in range(world))]
+    for r in range(world):
+        a, b = shard_range(240, r, world)
+        S, Gs = seeds_from_summaries(sums, r, policy)
+        assert np.abs(S - ref[a]).max() < 1e-9 * max(1, np.abs(ref[a]).max())
+        if policy and valid[:a].any():
+            assert np.array_equal(Gs, G[np.nonzero(valid[:a])[0][-1]])
+
+
+def _gloo_worker(rank, world, port, policy, q):
+    import torch.distributed as dist
+    from evenvizion_b200.distributed import all_gather_summaries
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    G, valid = _rand_chain(120, 7)
+    a, b = shard_range(120, rank, world)
+    mine = torch.from_numpy(_summary(G[a:b], valid[a:b], policy))
+    sums = all_gather_summaries(mine)
+    S, Gs = seeds_from_summaries(sums, rank, policy)
+    ref = chain.chain_products(chain.fill_none(G, valid, policy))
+    # seeded local chain == slice of the global chain
+    Gf = chain.fill_none(G[a:b], valid[a:b], policy)
+    if policy and Gs is not None:
+        lead = int(np.argmax(valid[a:b])) if valid[a:b].any() else b - a
+        Gf[:lead] = Gs
+    loc = chain.chain_products(Gf)
+    out = np.array([(S @ loc[i]) / (S @ loc[i])[2, 2] for i in range(1, len(loc))])
+    q.put((rank, float(np.abs(out - ref[a + 1:b + 1]).max())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("policy", [True, False])
+def test_two_rank_gloo_all_gather_seeding(policy):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + (1 if policy else 0)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, policy, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(r for r, _ in res) == [0, 1]
+    assert max(e for _, e in res) < 1e-9

@@ -52,6 +52,15 @@ extern "C" const char* evz_last_error(const evz_handle* h) { return h ? h->err :
 
 extern "C" int evz_sm_count(const evz_handle* h) { return h ? h->sm_count : 0; }
 
+extern "C" int evz_set_option(evz_handle* h, int option, int value) {
+    if (!h) return EVZ_E_ARG;
+    switch (option) {
+        case EVZ_OPT_RANSAC_EXACT: h->opt_ransac_exact = value; return EVZ_OK;
+        case EVZ_OPT_MATCH_VARIANT: h->opt_match_variant = value; return EVZ_OK;
+        default: EVZ_SET_ERR(h, "evz_set_option: unknown option %d", option); return EVZ_E_ARG;
+    }
+}
+
 int evz_scratch(evz_handle* h, size_t bytes, void** out) {
     if (bytes > h->scratch_bytes) {
         // growing is the one place the library synchronises: work queued on the old block must finish

@@ -25,6 +25,9 @@ struct evz_handle {
     int64_t tmap_rows = 0;
     evz_encode_tiled_fn encode = nullptr;
     bool match_attr_set = false;
+    // options (evz_set_option)
+    int opt_ransac_exact = 0;
+    int opt_match_variant = 0;
 };
 
 #define EVZ_SET_ERR(h, ...) do { if (h) snprintf((h)->err, sizeof((h)->err), __VA_ARGS__); } while (0)

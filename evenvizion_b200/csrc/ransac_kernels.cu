@@ -2,13 +2,20 @@
 // Replaces cv2.findHomography(a, b, cv2.RANSAC, thresh) (reference matching.py:156-157,
 // utils.py:356-358) and the 70 % gate of compute_homography (utils.py:359-360).
 //
+// ransac_score_kernel (256 threads, one CTA per pair)
 //   phase 1  every thread owns kHpt hypotheses at a time: counter-based PCG sample of 4 distinct
 //            matches, closed-form 4-point solve in f64 registers (projective basis), cast to f32;
 //   phase 2  all matches (float4 ax,ay,bx,by staged in shared memory) are scored against the
-//            thread's hypotheses: broadcast LDS.128, OpenCV's f32 computeError formula with
-//            individually rounded operations (explicit _rn intrinsics, IEEE reciprocal), inlier
-//            count in a register; block arg-max on (count desc, hypothesis asc);
-//   phase 3  inlier mask of the winner (warp ballot), then LM on the 8 free parameters in f64
+//            thread's hypotheses (broadcast LDS.128, inlier count in a register).  The inlier test is
+//            OpenCV's f32 computeError <= thresh^2 with individually rounded operations.  To avoid
+//            paying ~35 instructions for every evaluation, a fused (FFMA + rcp.approx, ~11
+//            instructions) value is computed first together with a per-hypothesis bound on its
+//            distance from the exactly-rounded value; only evaluations whose fused error lies inside
+//            [t - band, t + band] re-run the exact formula.  Counts are therefore bit-identical to
+//            evaluating the exact formula everywhere (EVZ_OPT_RANSAC_EXACT forces that, for tests);
+//            block arg-max on (count desc, hypothesis asc).
+// ransac_refit_kernel (128 threads, one CTA per pair)
+//   phase 3  inlier mask of the winner (exact formula), then LM on the 8 free parameters in f64
 //            with OpenCV's damping schedule, started from the winning model;
 //   phase 4  final mask = f32 error of the refined H <= thresh^2, inlier count, 70 % gate.
 //
@@ -19,7 +26,8 @@
 
 namespace evz {
 
-constexpr int kRsThreads = 256;
+constexpr int kRsThreads = 256;   // scoring kernel
+constexpr int kRfThreads = 128;   // refit kernel
 constexpr int kHpt = 4;           // hypotheses scored concurrently per thread
 constexpr int kLmMaxIters = 20;   // OpenCV uses 10 from a DLT start; we start from the 4-point model
 constexpr int kNSums = 32;        // 21 JtJ + 8 Jtr + S + max|r| (+1 pad)
@@ -121,6 +129,7 @@ struct FhArgs {
     int32_t* status; double* H; uint8_t* mask; int32_t* inl_cnt;
     int32_t* best_hyp; int32_t* best_cnt; uint8_t* mask_best; double* H_best;
     int max_cnt;
+    int exact_only;
 };
 
 // 8x8 SPD solve by Gaussian elimination with partial pivoting (robust to the semi-definite corner)
@@ -194,7 +203,7 @@ struct LmShared {
     double x[8], xd[8], d[8], A[64], v[8], D[8];
     double S, lam, lc;
     double sums[kNSums];
-    double wsum[kRsThreads / 32][kNSums];
+    double wsum[kRfThreads / 32][kNSums];
     int iter, go;
 };
 
@@ -223,32 +232,72 @@ __device__ void lm_accumulate(const double* h, const float4* pts, const uint8_t*
     __syncthreads();
     if (threadIdx.x < 31) {
         double t = L.wsum[0][threadIdx.x];
-        for (int w = 1; w < kRsThreads / 32; ++w)
+        for (int w = 1; w < kRfThreads / 32; ++w)
             t = (threadIdx.x == 30) ? fmax(t, L.wsum[w][threadIdx.x]) : t + L.wsum[w][threadIdx.x];
         L.sums[threadIdx.x] = t;
     }
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kRsThreads, 2)
-find_homography_kernel(const FhArgs a) {
+// fused (FFMA + approximate reciprocal) evaluation of the same quantity as reproj_err32
+__device__ __forceinline__ float reproj_err_fused(const float (&h)[8], const float4 p) {
+    const float den = __fmaf_rn(h[6], p.x, __fmaf_rn(h[7], p.y, 1.f));
+    float ww;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ww) : "f"(den));
+    const float X = __fmaf_rn(h[0], p.x, __fmaf_rn(h[1], p.y, h[2]));
+    const float Y = __fmaf_rn(h[3], p.x, __fmaf_rn(h[4], p.y, h[5]));
+    const float dx = __fmaf_rn(X, ww, -p.z);
+    const float dy = __fmaf_rn(Y, ww, -p.w);
+    return __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+}
+
+// Band around the threshold outside of which the fused value decides the exact test.
+// With u = 2^-24, |coords| <= cmax, dmin <= |den| (>= 0.5), Bx >= |h0 x| + |h1 y| + |h2|:
+//   rel. error of ww  (either path) <= rho = 4u Bd/dmin + 2u          (rcp.approx: 2^-23)
+//   |X ww - u| error  (either path) <= (Bx/dmin)(5u + rho) + u (Bx/dmin + cmax)
+// so the two paths differ by at most dX (dY) below, with a 1.25 safety factor, and
+// |err_exact - err_fused| <= (dX + dY) * 2 sqrt(err) + 3u err.  band = 8 (dX + dY) + 1e-5 covers it
+// for err near t = thresh^2 (sqrt ~ 3) and the margin only grows away from t (linear vs sqrt).
+__device__ __forceinline__ void fused_band(const float (&h)[8], float cmax, float t, bool usable, bool exact_only,
+                                           float& tlo, float& thi) {
+    const float u = 5.9604645e-8f;
+    const float a6 = fabsf(h[6]) + fabsf(h[7]);
+    const float dmin = 1.f - a6 * cmax;
+    const float Bd = a6 * cmax + 1.f;
+    const float Bx = (fabsf(h[0]) + fabsf(h[1])) * cmax + fabsf(h[2]);
+    const float By = (fabsf(h[3]) + fabsf(h[4])) * cmax + fabsf(h[5]);
+    const float rho = 4.f * u * Bd / dmin + 2.f * u;
+    const float dX = 2.5f * ((Bx / dmin) * (6.f * u + rho) + u * cmax);
+    const float dY = 2.5f * ((By / dmin) * (6.f * u + rho) + u * cmax);
+    const float D = dX + dY;
+    const float band = 8.f * D + 1e-5f;
+    const float nanv = __int_as_float(0x7fc00000);
+    if (!usable) { tlo = -INFINITY; thi = -INFINITY; return; }      // degenerate hypothesis: everything "sure out"
+    if (exact_only || !(dmin >= 0.5f) || !(D < 0.5f)) { tlo = nanv; thi = nanv; return; }   // every evaluation exact
+    tlo = t - band;
+    thi = t + band;
+}
+
+__global__ void __launch_bounds__(kRsThreads, 3)
+ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __restrict__ phase) {
     extern __shared__ __align__(16) uint8_t fh_smem[];
     float4* pts = reinterpret_cast<float4*>(fh_smem);
-    uint8_t* msk = fh_smem + static_cast<size_t>(a.max_cnt) * 16;
-    __shared__ LmShared L;
     __shared__ double Hbest[9];
     __shared__ unsigned long long red[kRsThreads / 32];
+    __shared__ float cmax_s[kRsThreads / 32];
     __shared__ int s_flag, s_cnt;
 
     const int p = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) phase[p] = 0;
     if (a.status[p] != EVZ_ST_OK) return;
     const int m = a.cnt[p];
     const int64_t o = a.off[p];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (m < 4) { if (tid == 0) a.status[p] = EVZ_ST_FEW_POINTS; return; }
 
-    // stage the point pairs (optionally through matrix_H_prev)
+    // stage the point pairs (optionally through matrix_H_prev); track max |coordinate|
     const double* T = a.pre_H ? a.pre_H + static_cast<size_t>(p) * 9 : nullptr;
+    float cmax = 0.f;
     for (int i = tid; i < m; i += blockDim.x) {
         float4 v = reinterpret_cast<const float4*>(a.pts)[o + i];
         if (T) {
@@ -256,11 +305,16 @@ find_homography_kernel(const FhArgs a) {
             v = make_float4(pa.x, pa.y, pb.x, pb.y);
         }
         pts[i] = v;
+        cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffff, cmax, of));
+    if (lane == 0) cmax_s[warp] = cmax;
     __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kRsThreads / 32; ++w) cmax = fmaxf(cmax, cmax_s[w]);
 
     const uint32_t pair_level = static_cast<uint32_t>((a.pair_id_base + p) * 2 + a.level);
-    int best_h = -1, best_c = 0;
     if (m == 4) {
         // findHomography: npoints == 4 -> exact model through the 4 points, mask = ones, no LM
         if (tid == 0) {
@@ -268,55 +322,69 @@ find_homography_kernel(const FhArgs a) {
             double H[9];
             solve4(q, H);
             bool fin = true;
-            for (int i = 0; i < 9; ++i) { Hbest[i] = H[i]; fin = fin && isfinite(H[i]); }
+            for (int i = 0; i < 9; ++i) fin = fin && isfinite(H[i]);
+            if (!fin) a.status[p] = a.fail_status;
+            else {
+                for (int i = 0; i < 9; ++i) { a.H[static_cast<size_t>(p) * 9 + i] = H[i]; Hbest_out[static_cast<size_t>(p) * 9 + i] = H[i]; }
+                if (a.best_hyp) a.best_hyp[p] = -1;
+                if (a.best_cnt) a.best_cnt[p] = 4;
+                if (a.inl_cnt) a.inl_cnt[p] = 4;
+            }
             s_flag = fin;
         }
         __syncthreads();
-        if (!s_flag) { if (tid == 0) a.status[p] = a.fail_status; return; }
-        if (tid < 4) { if (a.mask_best) a.mask_best[o + tid] = 1; if (a.mask) a.mask[o + tid] = 1; }
-        if (tid == 0) {
-            for (int i = 0; i < 9; ++i) { a.H[static_cast<size_t>(p) * 9 + i] = Hbest[i]; if (a.H_best) a.H_best[static_cast<size_t>(p) * 9 + i] = Hbest[i]; }
-            if (a.best_hyp) a.best_hyp[p] = -1;
-            if (a.best_cnt) a.best_cnt[p] = 4;
-            if (a.inl_cnt) a.inl_cnt[p] = 4;
-        }
+        if (s_flag && tid < 4) { if (a.mask_best) a.mask_best[o + tid] = 1; if (a.mask) a.mask[o + tid] = 1; }
         return;
     }
 
     // ---------------- phases 1 + 2: hypotheses
+    int best_h = -1, best_c = 0;
     for (int h0 = 0; h0 < a.n_hyp; h0 += kRsThreads * kHpt) {
         float hf[kHpt][8];
-        bool okh[kHpt];
+        float tlo[kHpt], thi[kHpt];
         int cnt[kHpt];
 #pragma unroll
         for (int j = 0; j < kHpt; ++j) {
             const int hyp = h0 + j * kRsThreads + tid;
             cnt[j] = 0;
-            okh[j] = false;
+            bool ok = false;
             if (hyp < a.n_hyp) {
                 int idx[4];
                 sample4(a.seed, pair_level, static_cast<uint32_t>(hyp), m, idx);
                 const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
                 double H[9];
-                okh[j] = solve4(q, H);
+                ok = solve4(q, H);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) hf[j][i] = static_cast<float>(H[i]);
+                for (int i = 0; i < 8; ++i) hf[j][i] = ok ? static_cast<float>(H[i]) : 0.f;
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) hf[j][i] = 0.f;
             }
+            fused_band(hf[j], cmax, a.thresh2, ok, a.exact_only != 0, tlo[j], thi[j]);
         }
         for (int i = 0; i < m; ++i) {
             const float4 pt = pts[i];
+            bool uns[kHpt];
+            bool any_uns = false;
 #pragma unroll
-            for (int j = 0; j < kHpt; ++j) cnt[j] += (reproj_err32(hf[j], pt) <= a.thresh2) ? 1 : 0;
+            for (int j = 0; j < kHpt; ++j) {
+                const float e = reproj_err_fused(hf[j], pt);
+                const bool in = e <= tlo[j];
+                cnt[j] += in ? 1 : 0;
+                uns[j] = !(in || e >= thi[j]);
+                any_uns = any_uns || uns[j];
+            }
+            if (__any_sync(0xffffffff, any_uns)) {
+#pragma unroll
+                for (int j = 0; j < kHpt; ++j)
+                    if (uns[j]) cnt[j] += (reproj_err32(hf[j], pt) <= a.thresh2) ? 1 : 0;
+            }
         }
 #pragma unroll
         for (int j = 0; j < kHpt; ++j) {
             const int hyp = h0 + j * kRsThreads + tid;
-            const int c = okh[j] ? cnt[j] : 0;
             // this thread visits its hypotheses in ascending order: strict > keeps the lowest index
-            if (hyp < a.n_hyp && c > best_c) { best_c = c; best_h = hyp; }
+            if (hyp < a.n_hyp && cnt[j] > best_c) { best_c = cnt[j]; best_h = hyp; }
         }
     }
     // block arg-max on (count desc, hypothesis asc): pack count high, ~hyp low
@@ -331,36 +399,58 @@ find_homography_kernel(const FhArgs a) {
         for (int w = 1; w < kRsThreads / 32; ++w) k = red[w] > k ? red[w] : k;
         const int bc = static_cast<int>(k >> 32);
         const int bh = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(k & 0xFFFFFFFFu));
-        s_cnt = bc;
-        s_flag = bh;
+        if (a.best_hyp) a.best_hyp[p] = bh;
+        if (a.best_cnt) a.best_cnt[p] = bc;
         if (bc >= 4) {
             int idx[4];
             sample4(a.seed, pair_level, static_cast<uint32_t>(bh), m, idx);
             const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
             double H[9];
             solve4(q, H);
-            for (int i = 0; i < 9; ++i) Hbest[i] = H[i];
+            for (int i = 0; i < 9; ++i) Hbest_out[static_cast<size_t>(p) * 9 + i] = H[i];
+            phase[p] = 1;
+        } else {
+            a.status[p] = a.fail_status;
         }
     }
+}
+
+__global__ void __launch_bounds__(kRfThreads)
+ransac_refit_kernel(const FhArgs a, const double* __restrict__ Hbest_in, const int32_t* __restrict__ phase) {
+    extern __shared__ __align__(16) uint8_t fh_smem[];
+    float4* pts = reinterpret_cast<float4*>(fh_smem);
+    uint8_t* msk = fh_smem + static_cast<size_t>(a.max_cnt) * 16;
+    __shared__ LmShared L;
+    __shared__ int red[kRfThreads / 32];
+
+    const int p = blockIdx.x;
+    if (phase[p] != 1) return;
+    const int m = a.cnt[p];
+    const int64_t o = a.off[p];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* T = a.pre_H ? a.pre_H + static_cast<size_t>(p) * 9 : nullptr;
+    for (int i = tid; i < m; i += blockDim.x) {
+        float4 v = reinterpret_cast<const float4*>(a.pts)[o + i];
+        if (T) {
+            const float2 pa = pre_map(T, v.x, v.y), pb = pre_map(T, v.z, v.w);
+            v = make_float4(pa.x, pa.y, pb.x, pb.y);
+        }
+        pts[i] = v;
+    }
+    if (tid < 8) L.x[tid] = Hbest_in[static_cast<size_t>(p) * 9 + tid];
     __syncthreads();
-    const int bcnt = s_cnt, bhyp = s_flag;
-    if (tid == 0) { if (a.best_hyp) a.best_hyp[p] = bhyp; if (a.best_cnt) a.best_cnt[p] = bcnt; }
-    if (bcnt < 4) { if (tid == 0) a.status[p] = a.fail_status; return; }
-    if (tid == 0 && a.H_best) for (int i = 0; i < 9; ++i) a.H_best[static_cast<size_t>(p) * 9 + i] = Hbest[i];
 
     // ---------------- phase 3: winner's inlier mask, then LM refit on it
     {
         float hb[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) hb[i] = static_cast<float>(Hbest[i]);
+        for (int i = 0; i < 8; ++i) hb[i] = static_cast<float>(L.x[i]);
         for (int i = tid; i < m; i += blockDim.x) {
             const uint8_t in = reproj_err32(hb, pts[i]) <= a.thresh2 ? 1 : 0;
             msk[i] = in;
             if (a.mask_best) a.mask_best[o + i] = in;
         }
     }
-    __syncthreads();
-    if (tid < 8) L.x[tid] = Hbest[tid];
     __syncthreads();
     lm_accumulate(L.x, pts, msk, m, L);
     if (tid == 0) {
@@ -439,12 +529,11 @@ find_homography_kernel(const FhArgs a) {
     }
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) c += __shfl_xor_sync(0xffffffff, c, of);
-    __syncthreads();
-    if (lane == 0) red[warp] = static_cast<unsigned long long>(c);
+    if (lane == 0) red[warp] = c;
     __syncthreads();
     if (tid == 0) {
         int tot = 0;
-        for (int w = 0; w < kRsThreads / 32; ++w) tot += static_cast<int>(red[w]);
+        for (int w = 0; w < kRfThreads / 32; ++w) tot += red[w];
         if (a.inl_cnt) a.inl_cnt[p] = tot;
         for (int i = 0; i < 8; ++i) a.H[static_cast<size_t>(p) * 9 + i] = L.x[i];
         a.H[static_cast<size_t>(p) * 9 + 8] = 1.0;
@@ -472,16 +561,30 @@ extern "C" int evz_find_homography(evz_handle* h, const float* pts, const int32_
     if (n_pairs <= 0) return EVZ_OK;
     if (max_cnt < 4) max_cnt = 4;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int smem = max_cnt * 17 + 16;
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
-        EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::find_homography_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
+    // scratch: phase[P] | H_best[P][9] when the caller does not want it
+    void* scr = nullptr;
+    const size_t ph_bytes = evz_align_up(static_cast<size_t>(n_pairs) * 4, 256);
+    int rc = evz_scratch(h, ph_bytes + (H_best ? 0 : static_cast<size_t>(n_pairs) * 72) + 256, &scr);
+    if (rc) return rc;
+    int32_t* phase = static_cast<int32_t*>(scr);
+    double* hb = H_best ? H_best : reinterpret_cast<double*>(static_cast<uint8_t*>(scr) + ph_bytes);
+    const int smem_score = max_cnt * 16 + 16;
+    const int smem_refit = max_cnt * 17 + 16;
+    static int attr_score = 0, attr_refit = 0;
+    if (smem_score > attr_score) {
+        EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::ransac_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_score));
+        attr_score = smem_score;
+    }
+    if (smem_refit > attr_refit) {
+        EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::ransac_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_refit));
+        attr_refit = smem_refit;
     }
     const float t = static_cast<float>(thresh * thresh);
     evz::FhArgs a{pts, off, cnt, pre_H, n_hyp, seed, pair_id_base, level, t, min_inlier_frac, fail_status,
-                  status, H, mask, inl_cnt, best_hyp, best_cnt, mask_best, H_best, max_cnt};
-    evz::find_homography_kernel<<<n_pairs, evz::kRsThreads, smem, st>>>(a);
+                  status, H, mask, inl_cnt, best_hyp, best_cnt, mask_best, H_best, max_cnt, h->opt_ransac_exact};
+    evz::ransac_score_kernel<<<n_pairs, evz::kRsThreads, smem_score, st>>>(a, hb, phase);
+    EVZ_LAUNCH_CHECK(h);
+    evz::ransac_refit_kernel<<<n_pairs, evz::kRfThreads, smem_refit, st>>>(a, hb, phase);
     EVZ_LAUNCH_CHECK(h);
     return EVZ_OK;
 }

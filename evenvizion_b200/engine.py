@@ -103,6 +103,10 @@ class GeometryEngine:
         except Exception:
             pass
 
+    def set_option(self, option: int, value: int):
+        """EVZ_OPT_* switches of include/evz.h (A/B routes with identical results)."""
+        self._check(self.lib.evz_set_option(self.h, int(option), int(value)))
+
     # ------------------------------------------------------------------ helpers
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

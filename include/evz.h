@@ -77,6 +77,11 @@ void        evz_destroy(evz_handle* h);
 const char* evz_last_error(const evz_handle* h);     /* h may be NULL: last creation error */
 int         evz_sm_count(const evz_handle* h);
 
+/* debugging / A-B options; results are identical for every setting, only the route differs */
+#define EVZ_OPT_RANSAC_EXACT   1  /* 1: score every hypothesis x match with the exactly-rounded formula (no fused fast path) */
+#define EVZ_OPT_MATCH_VARIANT  2  /* 0: default epilogue; 1: reference epilogue (full top-2 per element, no fix-up pass) */
+int         evz_set_option(evz_handle* h, int option, int value);
+
 /* ---- ingest: the step before the path.  Replaces the implicit
  * np.float32 -> cv::Mat conversion inside knnMatch (matching.py:108) and prepares
  * remove_double_matching's key comparison (utils.py:63-64).

@@ -128,3 +128,37 @@ def test_static_filter_vs_oracle(engine, golden):
     for i in range(int(golden["fh_n"])):      # and against the reference's own output
         g = out_pts[off_h[i]:off_h[i] + int(out_cnt[i])].cpu().numpy()
         assert np.array_equal(g[:, :2], golden[f"fh{i}_static_a"]) and np.array_equal(g[:, 2:], golden[f"fh{i}_static_b"])
+
+
+@pytest.mark.parametrize("scale,persp", [(1.0, 1e-5), (8.0, 1e-5), (1.0, 2e-4), (0.05, 1e-5)])
+def test_fused_fast_path_equals_exact_scoring(engine, scale, persp):
+    """The FFMA + rcp.approx classification must give the same inlier counts as the exactly
+    rounded formula everywhere (EVZ_OPT_RANSAC_EXACT forces the latter)."""
+    rng = np.random.default_rng(int(scale * 100) + int(persp * 1e6))
+    sets = []
+    for k in range(24):
+        n = int(rng.integers(200, 2000))
+        a = (rng.random((n, 2)) * [1920, 1080] * scale).astype(np.float32)
+        th = rng.normal() * 0.02
+        Ht = np.array([[np.cos(th), -np.sin(th), rng.normal() * 8 * scale], [np.sin(th), np.cos(th), rng.normal() * 8 * scale],
+                       [rng.normal() * persp / scale, rng.normal() * persp / scale, 1]])
+        p = np.c_[a, np.ones(n)] @ Ht.T
+        # residuals spread densely around the 3 px threshold to exercise the band
+        b = (p[:, :2] / p[:, 2:] + rng.normal(size=(n, 2)) * rng.choice([0.3, 1.5, 2.2], size=(n, 1))).astype(np.float32)
+        o = rng.random(n) < 0.3
+        b[o] = (rng.random((int(o.sum()), 2)) * [1920, 1080] * scale).astype(np.float32)
+        sets.append((a, b))
+    pts, off, cnt, off_h, cnt_h = _pack(sets, engine.device)
+    outs = []
+    for exact in (0, 1):
+        engine.set_option(1, exact)
+        status = torch.zeros(len(sets), dtype=torch.int32, device=engine.device)
+        outs.append((engine.find_homography(pts, off, cnt, status, int(cnt_h.max()), 2048, 3, 50, 1), status))
+    engine.set_option(1, 0)
+    (f, sf), (e, se) = outs
+    assert torch.equal(sf, se)
+    for k in ("best_hyp", "best_cnt", "mask_best", "H_best", "mask", "inl_cnt"):
+        assert torch.equal(f[k], e[k]), k
+    i = 3
+    ref = ransac.find_homography_seeded(sets[i][0], sets[i][1], 2048, 3, 50 + i, 1)
+    assert int(f["best_hyp"][i]) == ref["hyp"]["best"] and int(f["best_cnt"][i]) == ref["hyp"]["best_count"]

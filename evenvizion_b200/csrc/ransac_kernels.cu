@@ -251,41 +251,51 @@ __device__ __forceinline__ float reproj_err_fused(const float (&h)[8], const flo
     return __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
 }
 
-// Band around the threshold outside of which the fused value decides the exact test.
-// With u = 2^-24, |coords| <= cmax, dmin <= |den| (>= 0.5), Bx >= |h0 x| + |h1 y| + |h2|:
-//   rel. error of ww  (either path) <= rho = 4u Bd/dmin + 2u          (rcp.approx: 2^-23)
-//   |X ww - u| error  (either path) <= (Bx/dmin)(5u + rho) + u (Bx/dmin + cmax)
-// so the two paths differ by at most dX (dY) below, with a 1.25 safety factor, and
-// |err_exact - err_fused| <= (dX + dY) * 2 sqrt(err) + 3u err.  band = 8 (dX + dY) + 1e-5 covers it
-// for err near t = thresh^2 (sqrt ~ 3) and the margin only grows away from t (linear vs sqrt).
-__device__ __forceinline__ void fused_band(const float (&h)[8], float cmax, float t, bool usable, bool exact_only,
-                                           float& tlo, float& thi) {
+// Thresholds outside of which the fused value decides the exact test  err_exact <= t.
+// u = 2^-24; |coords| <= cmax; Bd >= |h6 x| + |h7 y| + 1; Bx >= |h0 x| + |h1 y| + |h2|; an evaluation
+// is only classified when |den_fused| >= kDenMin, so |den| >= dm = 0.9 kDenMin on both paths
+// (requires 8 u Bd <= 0.1 kDenMin).  Then, for either path,
+//   rel. error of ww            <= rho = 4u Bd/dm + 2u                     (rcp.approx: 2^-23)
+//   abs. error of X ww - u_i    <= (Bx/dm)(6u + rho) + u cmax
+// so the paths differ by at most dX (dY) below (x1.25 safety) and, with D = dX + dY,
+//   |err_exact - err_fused| <= 2 D sqrt(max err) + 6u max err.
+// Solving the two one-sided implications for the fused value gives
+//   err_fused >= t + 2D^2 + 2D sqrt(D^2 + t)  =>  err_exact >  t      (thi, margin x1.25 + 1e-4)
+//   err_fused <= t - 6D            (D < 2)    =>  err_exact <= t      (tlo, margin x1.25 + 1e-4)
+// Everything else (inside the band, |den| small, NaN) is "unsure" and counted in hi only.
+constexpr float kDenMin = 0.0625f;
+__device__ __forceinline__ void fused_thresholds(const float (&h)[8], float cmax, float t, bool exact_only,
+                                                 float& tlo, float& thi) {
     const float u = 5.9604645e-8f;
     const float a6 = fabsf(h[6]) + fabsf(h[7]);
-    const float dmin = 1.f - a6 * cmax;
     const float Bd = a6 * cmax + 1.f;
     const float Bx = (fabsf(h[0]) + fabsf(h[1])) * cmax + fabsf(h[2]);
     const float By = (fabsf(h[3]) + fabsf(h[4])) * cmax + fabsf(h[5]);
-    const float rho = 4.f * u * Bd / dmin + 2.f * u;
-    const float dX = 2.5f * ((Bx / dmin) * (6.f * u + rho) + u * cmax);
-    const float dY = 2.5f * ((By / dmin) * (6.f * u + rho) + u * cmax);
+    const float dm = 0.9f * kDenMin;
+    const float rho = 4.f * u * Bd / dm + 2.f * u;
+    const float dX = 2.5f * ((Bx / dm) * (6.f * u + rho) + u * cmax);
+    const float dY = 2.5f * ((By / dm) * (6.f * u + rho) + u * cmax);
     const float D = dX + dY;
-    const float band = 8.f * D + 1e-5f;
-    const float nanv = __int_as_float(0x7fc00000);
-    if (!usable) { tlo = -INFINITY; thi = -INFINITY; return; }      // degenerate hypothesis: everything "sure out"
-    if (exact_only || !(dmin >= 0.5f) || !(D < 0.5f)) { tlo = nanv; thi = nanv; return; }   // every evaluation exact
-    tlo = t - band;
-    thi = t + band;
+    tlo = -INFINITY;
+    thi = INFINITY;
+    if (exact_only || !(8.f * u * Bd <= 0.1f * kDenMin) || !(D < 1e6f)) return;      // no usable bound: all unsure
+    thi = t + 1.25f * (2.f * D * D + 2.f * D * sqrtf(D * D + t)) + 1e-4f;
+    if (D < 2.f) tlo = t - 1.25f * 6.f * D - 1e-4f;
 }
 
+// dynamic shared memory of the scoring kernel: float4 pts[max_cnt] | u16 vlist, slist, lo_s, hi_s [n_hyp] each
 __global__ void __launch_bounds__(kRsThreads, 3)
 ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __restrict__ phase) {
     extern __shared__ __align__(16) uint8_t fh_smem[];
     float4* pts = reinterpret_cast<float4*>(fh_smem);
-    __shared__ double Hbest[9];
+    uint16_t* vlist = reinterpret_cast<uint16_t*>(fh_smem + static_cast<size_t>(a.max_cnt) * 16);   // valid hypotheses
+    uint16_t* slist = vlist + a.n_hyp;                                                                // survivors to rescore
+    uint16_t* lo_s = slist + a.n_hyp;                                                                 // count bounds per valid slot
+    uint16_t* hi_s = lo_s + a.n_hyp;
     __shared__ unsigned long long red[kRsThreads / 32];
     __shared__ float cmax_s[kRsThreads / 32];
-    __shared__ int s_flag, s_cnt;
+    __shared__ int warp_sums[32];
+    __shared__ int s_flag, s_nvalid, s_nsurv, s_lbest;
 
     const int p = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -310,6 +320,7 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffff, cmax, of));
     if (lane == 0) cmax_s[warp] = cmax;
+    if (tid == 0) { s_nvalid = 0; s_nsurv = 0; s_lbest = 0; }
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < kRsThreads / 32; ++w) cmax = fmaxf(cmax, cmax_s[w]);
@@ -337,59 +348,125 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
         return;
     }
 
-    // ---------------- phases 1 + 2: hypotheses
-    int best_h = -1, best_c = 0;
-    for (int h0 = 0; h0 < a.n_hyp; h0 += kRsThreads * kHpt) {
-        float hf[kHpt][8];
-        float tlo[kHpt], thi[kHpt];
-        int cnt[kHpt];
-#pragma unroll
-        for (int j = 0; j < kHpt; ++j) {
-            const int hyp = h0 + j * kRsThreads + tid;
-            cnt[j] = 0;
-            bool ok = false;
+    // ---------------- pass 0: which hypotheses pass the orientation / collinearity test (ordered compaction)
+    {
+        int base = 0;
+        for (int h0 = 0; h0 < a.n_hyp; h0 += kRsThreads) {
+            const int hyp = h0 + tid;
+            int ok = 0;
             if (hyp < a.n_hyp) {
                 int idx[4];
                 sample4(a.seed, pair_level, static_cast<uint32_t>(hyp), m, idx);
                 const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
                 double H[9];
-                ok = solve4(q, H);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) hf[j][i] = ok ? static_cast<float>(H[i]) : 0.f;
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) hf[j][i] = 0.f;
+                ok = solve4(q, H) ? 1 : 0;
             }
-            fused_band(hf[j], cmax, a.thresh2, ok, a.exact_only != 0, tlo[j], thi[j]);
+            const unsigned bal = __ballot_sync(0xffffffff, ok);
+            if (lane == 0) warp_sums[warp] = __popc(bal);
+            __syncthreads();
+            int before = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kRsThreads / 32; ++w) { const int c = warp_sums[w]; before += w < warp ? c : 0; total += c; }
+            if (ok) vlist[base + before + __popc(bal & ((1u << lane) - 1u))] = static_cast<uint16_t>(hyp);
+            base += total;
+            __syncthreads();
+        }
+        if (tid == 0) s_nvalid = base;
+    }
+    __syncthreads();
+    const int n_valid = s_nvalid;
+
+    // ---------------- pass 1: fused scoring of the valid hypotheses with count bounds [lo, hi]
+    unsigned long long best_key = 0;      // (exact count << 32) | ~hyp   of hypotheses whose count is already exact
+    for (int s0 = 0; s0 < n_valid; s0 += kRsThreads * kHpt) {
+        float hf[kHpt][8];
+        float tlo[kHpt], thi[kHpt];
+        int lo[kHpt], hi[kHpt];
+#pragma unroll
+        for (int j = 0; j < kHpt; ++j) {
+            const int slot = s0 + j * kRsThreads + tid;
+            lo[j] = 0; hi[j] = 0;
+            tlo[j] = -INFINITY; thi[j] = -INFINITY;            // idle slot: everything "sure out"
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hf[j][i] = 0.f;
+            if (slot < n_valid) {
+                int idx[4];
+                sample4(a.seed, pair_level, static_cast<uint32_t>(vlist[slot]), m, idx);
+                const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
+                double H[9];
+                solve4(q, H);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hf[j][i] = static_cast<float>(H[i]);
+                fused_thresholds(hf[j], cmax, a.thresh2, a.exact_only != 0, tlo[j], thi[j]);
+            }
         }
         for (int i = 0; i < m; ++i) {
             const float4 pt = pts[i];
-            bool uns[kHpt];
-            bool any_uns = false;
 #pragma unroll
             for (int j = 0; j < kHpt; ++j) {
-                const float e = reproj_err_fused(hf[j], pt);
-                const bool in = e <= tlo[j];
-                cnt[j] += in ? 1 : 0;
-                uns[j] = !(in || e >= thi[j]);
-                any_uns = any_uns || uns[j];
-            }
-            if (__any_sync(0xffffffff, any_uns)) {
-#pragma unroll
-                for (int j = 0; j < kHpt; ++j)
-                    if (uns[j]) cnt[j] += (reproj_err32(hf[j], pt) <= a.thresh2) ? 1 : 0;
+                const float den = __fmaf_rn(hf[j][6], pt.x, __fmaf_rn(hf[j][7], pt.y, 1.f));
+                float ww;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ww) : "f"(den));
+                const float X = __fmaf_rn(hf[j][0], pt.x, __fmaf_rn(hf[j][1], pt.y, hf[j][2]));
+                const float Y = __fmaf_rn(hf[j][3], pt.x, __fmaf_rn(hf[j][4], pt.y, hf[j][5]));
+                const float dx = __fmaf_rn(X, ww, -pt.z);
+                const float dy = __fmaf_rn(Y, ww, -pt.w);
+                const float e = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+                const bool den_ok = fabsf(den) >= kDenMin;
+                lo[j] += (den_ok && e <= tlo[j]) ? 1 : 0;
+                hi[j] += (den_ok && e >= thi[j]) ? 0 : 1;
             }
         }
+        int my_lo = 0;
 #pragma unroll
         for (int j = 0; j < kHpt; ++j) {
-            const int hyp = h0 + j * kRsThreads + tid;
-            // this thread visits its hypotheses in ascending order: strict > keeps the lowest index
-            if (hyp < a.n_hyp && cnt[j] > best_c) { best_c = cnt[j]; best_h = hyp; }
+            const int slot = s0 + j * kRsThreads + tid;
+            if (slot < n_valid) { lo_s[slot] = static_cast<uint16_t>(lo[j]); hi_s[slot] = static_cast<uint16_t>(hi[j]); }
+            my_lo = max(my_lo, lo[j]);
+        }
+        atomicMax(&s_lbest, my_lo);
+    }
+    __syncthreads();
+    const int lbest = s_lbest;
+    // hypotheses that can still be the arg-max: hi >= lbest.  Exact already if hi == lo, else rescore.
+    for (int slot = tid; slot < n_valid; slot += kRsThreads) {
+        const int lo = lo_s[slot], hi = hi_s[slot];
+        if (hi >= lbest && hi > 0) {
+            if (hi == lo) {
+                const unsigned long long key = (static_cast<unsigned long long>(static_cast<uint32_t>(lo)) << 32) |
+                                               (0xFFFFFFFFu - static_cast<uint32_t>(vlist[slot]));
+                best_key = key > best_key ? key : best_key;
+            } else {
+                slist[atomicAdd(&s_nsurv, 1)] = vlist[slot];
+            }
         }
     }
-    // block arg-max on (count desc, hypothesis asc): pack count high, ~hyp low
-    unsigned long long key = best_h < 0 ? 0ull
-        : (static_cast<unsigned long long>(static_cast<uint32_t>(best_c)) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(best_h));
+    __syncthreads();
+
+    // ---------------- pass 2: exact rescoring of the survivors, one warp per hypothesis, ballot / popc counts
+    const int n_surv = s_nsurv;
+    for (int k = warp; k < n_surv; k += kRsThreads / 32) {
+        const int hyp = slist[k];
+        int idx[4];
+        sample4(a.seed, pair_level, static_cast<uint32_t>(hyp), m, idx);
+        const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
+        double H[9];
+        solve4(q, H);
+        float hf[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hf[i] = static_cast<float>(H[i]);
+        int c = 0;
+        for (int i0 = 0; i0 < m; i0 += 32) {
+            const int i = i0 + lane;
+            const bool in = i < m && reproj_err32(hf, pts[i]) <= a.thresh2;
+            c += __popc(__ballot_sync(0xffffffff, in));
+        }
+        const unsigned long long key = (static_cast<unsigned long long>(static_cast<uint32_t>(c)) << 32) |
+                                       (0xFFFFFFFFu - static_cast<uint32_t>(hyp));
+        if (c > 0) best_key = key > best_key ? key : best_key;
+    }
+    // block arg-max on (count desc, hypothesis asc)
+    unsigned long long key = best_key;
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) { const unsigned long long u = __shfl_xor_sync(0xffffffff, key, of); key = u > key ? u : key; }
     if (lane == 0) red[warp] = key;
@@ -398,7 +475,7 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
         unsigned long long k = red[0];
         for (int w = 1; w < kRsThreads / 32; ++w) k = red[w] > k ? red[w] : k;
         const int bc = static_cast<int>(k >> 32);
-        const int bh = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(k & 0xFFFFFFFFu));
+        const int bh = k ? static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(k & 0xFFFFFFFFu)) : -1;
         if (a.best_hyp) a.best_hyp[p] = bh;
         if (a.best_cnt) a.best_cnt[p] = bc;
         if (bc >= 4) {
@@ -568,7 +645,8 @@ extern "C" int evz_find_homography(evz_handle* h, const float* pts, const int32_
     if (rc) return rc;
     int32_t* phase = static_cast<int32_t*>(scr);
     double* hb = H_best ? H_best : reinterpret_cast<double*>(static_cast<uint8_t*>(scr) + ph_bytes);
-    const int smem_score = max_cnt * 16 + 16;
+    EVZ_REQUIRE(h, n_hyp <= 65535, "n_hyp must be below 65536");
+    const int smem_score = max_cnt * 16 + 8 * n_hyp + 16;
     const int smem_refit = max_cnt * 17 + 16;
     static int attr_score = 0, attr_refit = 0;
     if (smem_score > attr_score) {

@@ -252,9 +252,11 @@ __device__ __forceinline__ float reproj_err_fused(const float (&h)[8], const flo
 }
 
 // Thresholds outside of which the fused value decides the exact test  err_exact <= t.
-// u = 2^-24; |coords| <= cmax; Bd >= |h6 x| + |h7 y| + 1; Bx >= |h0 x| + |h1 y| + |h2|; an evaluation
-// is only classified when |den_fused| >= kDenMin, so |den| >= dm = 0.9 kDenMin on both paths
-// (requires 8 u Bd <= 0.1 kDenMin).  Then, for either path,
+// u = 2^-24; |coords| <= cmax; Bd >= |h6 x| + |h7 y| + 1; Bx >= |h0 x| + |h1 y| + |h2|.  Over the
+// data range den >= 1 - (|h6|+|h7|) cmax; in addition an evaluation is only classified when
+// |den_fused| >= kDenMin.  With the 8 u Bd rounding slack both give |den| >= dm on both paths
+//   dm = max(0.9 kDenMin, 1 - (|h6|+|h7|) cmax - 8 u Bd)        (requires 8 u Bd <= 0.1 kDenMin).
+// Then, for either path,
 //   rel. error of ww            <= rho = 4u Bd/dm + 2u                     (rcp.approx: 2^-23)
 //   abs. error of X ww - u_i    <= (Bx/dm)(6u + rho) + u cmax
 // so the paths differ by at most dX (dY) below (x1.25 safety) and, with D = dX + dY,
@@ -271,7 +273,7 @@ __device__ __forceinline__ void fused_thresholds(const float (&h)[8], float cmax
     const float Bd = a6 * cmax + 1.f;
     const float Bx = (fabsf(h[0]) + fabsf(h[1])) * cmax + fabsf(h[2]);
     const float By = (fabsf(h[3]) + fabsf(h[4])) * cmax + fabsf(h[5]);
-    const float dm = 0.9f * kDenMin;
+    const float dm = fmaxf(0.9f * kDenMin, (1.f - a6 * cmax - 8.f * u * Bd) * 0.999999f);
     const float rho = 4.f * u * Bd / dm + 2.f * u;
     const float dX = 2.5f * ((Bx / dm) * (6.f * u + rho) + u * cmax);
     const float dY = 2.5f * ((By / dm) * (6.f * u + rho) + u * cmax);
@@ -381,11 +383,11 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     for (int s0 = 0; s0 < n_valid; s0 += kRsThreads * kHpt) {
         float hf[kHpt][8];
         float tlo[kHpt], thi[kHpt];
-        int lo[kHpt], hi[kHpt];
+        int lo[kHpt], hi[kHpt], out[kHpt];
 #pragma unroll
         for (int j = 0; j < kHpt; ++j) {
             const int slot = s0 + j * kRsThreads + tid;
-            lo[j] = 0; hi[j] = 0;
+            lo[j] = 0; hi[j] = 0; out[j] = 0;
             tlo[j] = -INFINITY; thi[j] = -INFINITY;            // idle slot: everything "sure out"
 #pragma unroll
             for (int i = 0; i < 8; ++i) hf[j][i] = 0.f;
@@ -412,11 +414,14 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
                 const float dx = __fmaf_rn(X, ww, -pt.z);
                 const float dy = __fmaf_rn(Y, ww, -pt.w);
                 const float e = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
-                const bool den_ok = fabsf(den) >= kDenMin;
-                lo[j] += (den_ok && e <= tlo[j]) ? 1 : 0;
-                hi[j] += (den_ok && e >= thi[j]) ? 0 : 1;
+                // |den| too small: not classifiable -> NaN fails both tests below (counted as unsure)
+                const float e2 = fabsf(den) >= kDenMin ? e : __int_as_float(0x7fc00000);
+                asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(lo[j]) : "f"(e2), "f"(tlo[j]));
+                asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(out[j]) : "f"(e2), "f"(thi[j]));
             }
         }
+#pragma unroll
+        for (int j = 0; j < kHpt; ++j) hi[j] = m - out[j];
         int my_lo = 0;
 #pragma unroll
         for (int j = 0; j < kHpt; ++j) {

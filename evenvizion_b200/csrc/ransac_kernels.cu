@@ -27,7 +27,7 @@
 namespace evz {
 
 constexpr int kRsThreads = 256;   // scoring kernel
-constexpr int kRfThreads = 128;   // refit kernel
+constexpr int kRfThreads = 64;    // refit kernel
 constexpr int kHpt = 4;           // hypotheses scored concurrently per thread
 constexpr int kLmMaxIters = 20;   // OpenCV uses 10 from a DLT start; we start from the 4-point model
 constexpr int kNSums = 32;        // 21 JtJ + 8 Jtr + S + max|r| (+1 pad)
@@ -132,27 +132,45 @@ struct FhArgs {
     int exact_only;
 };
 
-// 8x8 SPD solve by Gaussian elimination with partial pivoting (robust to the semi-definite corner)
-__device__ bool solve8(const double* A /*sym full 8x8*/, const double* b, double* x) {
-    double M[8][9];
-    for (int i = 0; i < 8; ++i) { for (int j = 0; j < 8; ++j) M[i][j] = A[i * 8 + j]; M[i][8] = b[i]; }
-    for (int c = 0; c < 8; ++c) {
-        int piv = c; double best = fabs(M[c][c]);
-        for (int r = c + 1; r < 8; ++r) if (fabs(M[r][c]) > best) { best = fabs(M[r][c]); piv = r; }
-        if (!(best > 0.0)) return false;
-        if (piv != c) for (int j = c; j < 9; ++j) { const double t = M[c][j]; M[c][j] = M[piv][j]; M[piv][j] = t; }
-        const double inv = 1.0 / M[c][c];
-        for (int r = c + 1; r < 8; ++r) {
-            const double f = M[r][c] * inv;
-            for (int j = c; j < 9; ++j) M[r][j] -= f * M[c][j];
+// 8x8 symmetric positive-definite system through an LDL^T factorisation held in registers
+// (all loops unrolled -> static indexing).  A: full symmetric 8x8 (shared memory), diag_add added to
+// the diagonal.  Returns false when a pivot is not positive / finite.
+struct Ldl8 { double L[8][8]; double d[8]; bool ok; };
+__device__ __forceinline__ void ldl8_factor(const double* A, const double* diag_add, double lam, Ldl8& f) {
+    f.ok = true;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        double dj = A[j * 8 + j] + (diag_add ? lam * diag_add[j] : 0.0);
+#pragma unroll
+        for (int k = 0; k < j; ++k) dj -= f.L[j][k] * f.L[j][k] * f.d[k];
+        f.ok = f.ok && (dj > 0.0) && isfinite(dj);
+        f.d[j] = dj;
+        const double inv = 1.0 / dj;
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i) {
+            double v = A[i * 8 + j];
+#pragma unroll
+            for (int k = 0; k < j; ++k) v -= f.L[i][k] * f.L[j][k] * f.d[k];
+            f.L[i][j] = v * inv;
         }
     }
-    for (int i = 7; i >= 0; --i) {
-        double s = M[i][8];
-        for (int j = i + 1; j < 8; ++j) s -= M[i][j] * x[j];
-        x[i] = s / M[i][i];
+}
+__device__ __forceinline__ void ldl8_solve(const Ldl8& f, const double (&b)[8], double (&x)[8]) {
+    double y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        double v = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) v -= f.L[i][k] * y[k];
+        y[i] = v;
     }
-    return true;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        double v = y[i] / f.d[i];
+#pragma unroll
+        for (int k = i + 1; k < 8; ++k) v -= f.L[k][i] * x[k];
+        x[i] = v;
+    }
 }
 
 // index of (i, j), i <= j, in the packed accumulators described in lm_accumulate
@@ -200,7 +218,7 @@ __device__ void lm_expand(const double* s, double* A, double* v) {
 }
 
 struct LmShared {
-    double x[8], xd[8], d[8], A[64], v[8], D[8];
+    double x[8], A[64], v[8], D[8];
     double S, lam, lc;
     double sums[kNSums];
     double wsum[kRfThreads / 32][kNSums];
@@ -497,7 +515,7 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     }
 }
 
-__global__ void __launch_bounds__(kRfThreads)
+__global__ void __launch_bounds__(kRfThreads, 6)
 ransac_refit_kernel(const FhArgs a, const double* __restrict__ Hbest_in, const int32_t* __restrict__ phase) {
     extern __shared__ __align__(16) uint8_t fh_smem[];
     float4* pts = reinterpret_cast<float4*>(fh_smem);
@@ -544,25 +562,28 @@ ransac_refit_kernel(const FhArgs a, const double* __restrict__ Hbest_in, const i
     }
     __syncthreads();
     while (L.go) {
-        if (tid == 0) {
-            double Ap[64];
-            for (int i = 0; i < 64; ++i) Ap[i] = L.A[i];
-            for (int i = 0; i < 8; ++i) Ap[i * 8 + i] += L.lam * L.D[i];
-            double d[8];
-            if (!solve8(Ap, L.v, d)) for (int i = 0; i < 8; ++i) d[i] = 0.0;
-            for (int i = 0; i < 8; ++i) { L.d[i] = d[i]; L.xd[i] = L.x[i] - d[i]; }
+        // every thread solves (A + lambda diag(D)) d = v redundantly in registers: no serial section
+        double d[8], xd[8];
+        {
+            Ldl8 f;
+            ldl8_factor(L.A, L.D, L.lam, f);
+            double vv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] = L.v[i];
+            ldl8_solve(f, vv, d);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { if (!f.ok) d[i] = 0.0; xd[i] = L.x[i] - d[i]; }
         }
-        __syncthreads();
-        lm_accumulate(L.xd, pts, msk, m, L);
+        lm_accumulate(xd, pts, msk, m, L);
         if (tid == 0) {
             const double Sd = L.sums[29];
             double dS = 0.0, tdv = 0.0, dmax = 0.0;
             for (int i = 0; i < 8; ++i) {
                 double Ad = 0.0;
-                for (int j = 0; j < 8; ++j) Ad += L.A[i * 8 + j] * L.d[j];
-                dS += L.d[i] * (2.0 * L.v[i] - Ad);
-                tdv += L.d[i] * L.v[i];
-                dmax = fmax(dmax, fabs(L.d[i]));
+                for (int j = 0; j < 8; ++j) Ad += L.A[i * 8 + j] * d[j];
+                dS += d[i] * (2.0 * L.v[i] - Ad);
+                tdv += d[i] * L.v[i];
+                dmax = fmax(dmax, fabs(d[i]));
             }
             const double R = (L.S - Sd) / (fabs(dS) > DBL_EPSILON ? dS : 1.0);
             if (R > 0.75) {
@@ -574,10 +595,19 @@ ransac_refit_kernel(const FhArgs a, const double* __restrict__ Hbest_in, const i
                 if (L.lam == 0.0) {
                     // lambda = lc = 1 / max |diag(A^-1)|
                     double maxval = DBL_EPSILON;
-                    for (int c = 0; c < 8; ++c) {
-                        double e[8], col[8];
-                        for (int i = 0; i < 8; ++i) e[i] = i == c ? 1.0 : 0.0;
-                        if (solve8(L.A, e, col)) maxval = fmax(maxval, fabs(col[c]));
+                    Ldl8 f;
+                    ldl8_factor(L.A, nullptr, 0.0, f);
+                    if (f.ok) {
+                        for (int c = 0; c < 8; ++c) {
+                            double e[8], col[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) e[i] = i == c ? 1.0 : 0.0;
+                            ldl8_solve(f, e, col);
+                            double cc = 0.0;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) cc = i == c ? col[i] : cc;
+                            maxval = fmax(maxval, fabs(cc));
+                        }
                     }
                     L.lam = L.lc = 1.0 / maxval;
                     nu *= 0.5;
@@ -587,7 +617,7 @@ ransac_refit_kernel(const FhArgs a, const double* __restrict__ Hbest_in, const i
             double rmax = 0.0;
             if (Sd < L.S) {
                 L.S = Sd;
-                for (int i = 0; i < 8; ++i) L.x[i] = L.xd[i];
+                for (int i = 0; i < 8; ++i) L.x[i] = xd[i];
                 lm_expand(L.sums, L.A, L.v);
                 rmax = L.sums[30];
             } else {

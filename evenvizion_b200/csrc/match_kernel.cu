@@ -9,13 +9,22 @@
 // while the tensor core fills acc[1].
 //
 // Epilogue, per accumulator element (row r = query, column c = train):
-//   key = ckey[c] - 512 * acc = ((||t_c||^2 - 2 q.t_c) << 8) | c      (one IMAD)
+//   key = ckey[c] - 512 * acc = ((||t_c||^2 - 2 q.t_c) << 8) | c      (one IMAD on the FMA pipe; the
+//   multiplier is a kernel argument so that ptxas cannot strength-reduce it onto the ALU pipe)
 // ckey[c] = (||t_c||^2 << 8) | (c & 255) comes from the frame store, INT32_MAX for padding rows;
 // it is staged next to the train tile by a 1 KB bulk copy.  ||t||^2 - 2 q.t >= -||q||^2 >= -8323200,
 // so the key fits in int32, and a signed min over keys is the lexicographic (distance, index)
 // minimum: ties go to the lowest train index exactly as OpenCV's batchDistance does.  ||q||^2 is
 // added once per row after the reduction.  A running top-2 per row is merged across tiles on
 // (value, frame-local index).
+//
+// The ALU pipe (min/max) bounds the epilogue, so the default variant does not track an exact top-2
+// per element.  It reduces every aligned chunk of 8 columns to its minimum with 3-input mins
+// (4 ops / 8 elements) and keeps the two smallest CHUNK minima (3 ops / 8 elements).  The smallest
+// is the exact nearest neighbour; the second neighbour is either the other chunk minimum or one of
+// the 7 remaining columns of the winning chunk, which a per-row fix-up at the end of the item
+// recomputes exactly (u8 dp4a, query row from the swizzled smem tile, 1 KB of train rows from L2).
+// Variant 1 (EVZ_OPT_MATCH_VARIANT) is the straightforward exact top-2 per element, kept for A/B.
 //
 // Warp roles (384 threads, 1 CTA / SM, persistent over items):
 //   warp 0 : TMA producer        warp 1 : MMA issuer       warp 2 : TMEM allocator
@@ -42,8 +51,8 @@ struct MatchSmem {
     static constexpr int q_off     = 0;                               // 2 x 32 KB
     static constexpr int t_off     = q_off + 2 * kQBytes;             // kStages x 32 KB
     static constexpr int ckey_off  = t_off + kStages * kTileBytes;    // kStages x 1 KB
-    static constexpr int merge_off = ckey_off + kStages * kCkeyBytes; // 256 rows x int4
-    static constexpr int bar_off   = merge_off + 256 * 16;
+    static constexpr int merge_off = ckey_off + kStages * kCkeyBytes; // 2 x 256 rows x int4
+    static constexpr int bar_off   = merge_off + 2 * 256 * 16;
     static constexpr int n_bars    = 2 * kStages + 2 + 2 + 2 + 2;
     static constexpr int tmem_off  = bar_off + n_bars * 8;
     static constexpr int total     = tmem_off + 16;
@@ -61,6 +70,8 @@ struct MatchArgs {
     const int32_t* n_items;    // device scalar
     int32_t* top2_idx;
     int32_t* top2_d2;
+    const uint8_t* desc;       // frame store descriptors (fix-up reads train rows through L2)
+    int neg512;                // -512, passed at run time (see header)
 };
 
 struct Item {
@@ -123,6 +134,78 @@ __device__ __forceinline__ void drain_half(uint32_t taddr, const int32_t* ck, in
     m2 = __vimin3_s32(max(a1, b1), a2, b2);
 }
 
+__device__ __forceinline__ int mad_key(uint32_t acc, int mul, int ck) {
+    int r;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(static_cast<int>(acc)), "r"(mul), "r"(ck));
+    return r;
+}
+// minimum packed key of 8 consecutive columns: 3 x min3 + 1 x min
+__device__ __forceinline__ int chunk_min8(const uint32_t* r, const int4 ka, const int4 kb, int mul) {
+    const int m0 = __vimin3_s32(mad_key(r[0], mul, ka.x), mad_key(r[1], mul, ka.y), mad_key(r[2], mul, ka.z));
+    const int m1 = __vimin3_s32(mad_key(r[3], mul, ka.w), mad_key(r[4], mul, kb.x), mad_key(r[5], mul, kb.y));
+    return __vimin3_s32(m0, m1, min(mad_key(r[6], mul, kb.z), mad_key(r[7], mul, kb.w)));
+}
+__device__ __forceinline__ void top2_one(int k, int& m1, int& m2) {
+    m2 = min(m2, max(m1, k));
+    m1 = min(m1, k);
+}
+// drain one 128-column half into the two smallest CHUNK minima (chunks of 8 columns)
+__device__ __forceinline__ void drain_half_chunked(uint32_t taddr, const int32_t* ck, int mul, int& m1, int& m2) {
+    int a1 = INT_MAX, a2 = INT_MAX, b1 = INT_MAX, b2 = INT_MAX;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(taddr + c * 64, r0);
+        tmem_ld_32x32b_x32(taddr + c * 64 + 32, r1);
+        tmem_ld_wait();
+        const int4* ck4 = reinterpret_cast<const int4*>(ck + c * 64);
+#pragma unroll
+        for (int q = 0; q < 4; q += 2) {
+            top2_one(chunk_min8(r0 + 8 * q, ck4[2 * q], ck4[2 * q + 1], mul), a1, a2);
+            top2_one(chunk_min8(r0 + 8 * q + 8, ck4[2 * q + 2], ck4[2 * q + 3], mul), b1, b2);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q += 2) {
+            top2_one(chunk_min8(r1 + 8 * q, ck4[8 + 2 * q], ck4[8 + 2 * q + 1], mul), a1, a2);
+            top2_one(chunk_min8(r1 + 8 * q + 8, ck4[8 + 2 * q + 2], ck4[8 + 2 * q + 3], mul), b1, b2);
+        }
+    }
+    m1 = min(a1, b1);
+    m2 = __vimin3_s32(max(a1, b1), a2, b2);
+}
+
+// exact second neighbour: the 7 other columns of the winning chunk against (V2, I2)
+__device__ __forceinline__ void fixup_second(const uint8_t* q_tile, int r, const uint8_t* desc, const int32_t* ckey,
+                                             int t_row0, int I1, int& V2, int& I2) {
+    const int cb = I1 & ~7;
+    const uint4* trow = reinterpret_cast<const uint4*>(desc + (static_cast<size_t>(t_row0) + cb) * kRowBytes);
+    unsigned int dot[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dot[j] = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 qv = *reinterpret_cast<const uint4*>(q_tile + r * kRowBytes + ((c ^ (r & 7)) << 4));   // SWIZZLE_128B
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint4 tv = __ldg(trow + j * 8 + c);
+            dot[j] = __dp4a(qv.x, tv.x, dot[j]); dot[j] = __dp4a(qv.y, tv.y, dot[j]);
+            dot[j] = __dp4a(qv.z, tv.z, dot[j]); dot[j] = __dp4a(qv.w, tv.w, dot[j]);
+        }
+    }
+    const int4 k0 = __ldg(reinterpret_cast<const int4*>(ckey + t_row0 + cb));
+    const int4 k1 = __ldg(reinterpret_cast<const int4*>(ckey + t_row0 + cb) + 1);
+    const int ck[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (cb + j != I1 && ck[j] != INT_MAX) {
+            const int v = (ck[j] >> 8) - 2 * static_cast<int>(dot[j]);
+            const int idx = cb + j;
+            if (v < V2 || (v == V2 && idx < I2) || I2 < 0) { V2 = v; I2 = idx; }
+        }
+    }
+}
+
+template <int kVariant>
 __global__ void __launch_bounds__(kThreads, 1)
 match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args) {
     extern __shared__ uint8_t smem_raw[];
@@ -147,7 +230,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args
         tma_prefetch_desc(&tmap);
         for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + kEpiWarps); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1);
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1 + kEpiWarps);
             mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps);
         }
         fence_mbar_init();
@@ -222,9 +305,12 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args
         const int quarter = warp & 3;           // TMEM lane quarter this warp may read
         const int half = e >> 2;                // column half of the accumulator
         const int row_in_sub = quarter * 32 + lane;
-        uint32_t stage = 0, sphase = 0, g = 0;
+        uint32_t stage = 0, sphase = 0, g = 0, qi = 0;
+        int4* merge2_s = merge_s + 256;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             const Item im = load_item(args, it);
+            const uint32_t qb = qi & 1;
+            if (im.n_tiles > 0) ++qi;
             int V1[2] = {INT_MAX, INT_MAX}, I1[2] = {-1, -1}, V2[2] = {INT_MAX, INT_MAX}, I2[2] = {-1, -1};
             for (int n = 0; n < im.n_tiles; ++n) {
                 mbar_wait(&full[stage], sphase);          // ckey tile visible to this thread
@@ -236,7 +322,9 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args
                         mbar_wait(&acc_full[acc], aph);
                         tc_fence_after();
                         int m1, m2;
-                        drain_half(tmem_base + acc * kBlockT + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16), ck, m1, m2);
+                        const uint32_t taddr = tmem_base + acc * kBlockT + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
+                        if (kVariant == 0) drain_half_chunked(taddr, ck, args.neg512, m1, m2);
+                        else               drain_half(taddr, ck, m1, m2);
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -249,7 +337,7 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args
                 if (lane == 0) mbar_arrive(&empty[stage]);
                 if (++stage == kStages) { stage = 0; sphase ^= 1; }
             }
-            // merge the two column halves through shared memory; half 0 writes the result
+            // merge the two column halves through shared memory
             if (half == 1) {
                 merge_s[row_in_sub] = make_int4(V1[0], I1[0], V2[0], I2[0]);
                 merge_s[128 + row_in_sub] = make_int4(V1[1], I1[1], V2[1], I2[1]);
@@ -258,22 +346,48 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args
             if (half == 0) {
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
-                    const int r = sub * 128 + row_in_sub;
-                    if (r < im.nq_left) {
-                        const int4 o = merge_s[r];
-                        if (o.y >= 0) top2_insert(o.x, o.y, V1[sub], I1[sub], V2[sub], I2[sub]);
-                        if (o.w >= 0) top2_insert(o.z, o.w, V1[sub], I1[sub], V2[sub], I2[sub]);
-                        const int qn = args.ckey[im.q_row0 + r] >> 8;
-                        const int64_t o_row = static_cast<int64_t>(im.out_row0) + r;
-                        int2 oi, od;
-                        oi.x = I1[sub]; od.x = I1[sub] >= 0 ? V1[sub] + qn : -1;
-                        oi.y = I2[sub]; od.y = I2[sub] >= 0 ? V2[sub] + qn : -1;
-                        reinterpret_cast<int2*>(args.top2_idx)[o_row] = oi;
-                        reinterpret_cast<int2*>(args.top2_d2)[o_row] = od;
-                    }
+                    const int4 o = merge_s[sub * 128 + row_in_sub];
+                    if (o.y >= 0) top2_insert(o.x, o.y, V1[sub], I1[sub], V2[sub], I2[sub]);
+                    if (o.w >= 0) top2_insert(o.z, o.w, V1[sub], I1[sub], V2[sub], I2[sub]);
+                    if (kVariant == 0) merge2_s[sub * 128 + row_in_sub] = make_int4(V1[sub], I1[sub], V2[sub], I2[sub]);
                 }
             }
-            named_bar_sync(1, kEpiWarps * 32);
+            if (kVariant == 0) {
+                // second barrier: the merged candidates are visible; warps of column half h finish the rows of sub-tile h
+                named_bar_sync(1, kEpiWarps * 32);
+                const int r = half * 128 + row_in_sub;
+                if (r < im.nq_left) {
+                    const int4 o = merge2_s[r];
+                    int v1 = o.x, i1 = o.y, v2 = o.z, i2 = o.w;
+                    if (i1 >= 0) fixup_second(q_s + qb * kQBytes, r, args.desc, args.ckey, im.t_row0, i1, v2, i2);
+                    const int qn = args.ckey[im.q_row0 + r] >> 8;
+                    const int64_t o_row = static_cast<int64_t>(im.out_row0) + r;
+                    int2 oi, od;
+                    oi.x = i1; od.x = i1 >= 0 ? v1 + qn : -1;
+                    oi.y = i2; od.y = i2 >= 0 ? v2 + qn : -1;
+                    reinterpret_cast<int2*>(args.top2_idx)[o_row] = oi;
+                    reinterpret_cast<int2*>(args.top2_d2)[o_row] = od;
+                }
+            } else {
+                if (half == 0) {
+#pragma unroll
+                    for (int sub = 0; sub < 2; ++sub) {
+                        const int r = sub * 128 + row_in_sub;
+                        if (r < im.nq_left) {
+                            const int qn = args.ckey[im.q_row0 + r] >> 8;
+                            const int64_t o_row = static_cast<int64_t>(im.out_row0) + r;
+                            int2 oi, od;
+                            oi.x = I1[sub]; od.x = I1[sub] >= 0 ? V1[sub] + qn : -1;
+                            oi.y = I2[sub]; od.y = I2[sub] >= 0 ? V2[sub] + qn : -1;
+                            reinterpret_cast<int2*>(args.top2_idx)[o_row] = oi;
+                            reinterpret_cast<int2*>(args.top2_d2)[o_row] = od;
+                        }
+                    }
+                }
+                named_bar_sync(1, kEpiWarps * 32);
+            }
+            // the query tile in shared memory may now be overwritten (the fix-up read it)
+            if (im.n_tiles > 0) { __syncwarp(); if (lane == 0) mbar_arrive(&q_empty[qb]); }
         }
     }
 
@@ -371,11 +485,15 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
     evz::build_items_kernel<<<1, 1024, 0, st>>>(n_kp, pair_q, n_pairs, items, n_items, static_cast<int>(capacity));
     EVZ_LAUNCH_CHECK(h);
     if (!h->match_attr_set) {
-        EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::kMatchSmemBytes));
+        EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::kMatchSmemBytes));
+        EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::kMatchSmemBytes));
         h->match_attr_set = true;
     }
-    evz::MatchArgs a{ckey, row_off, n_kp, pair_q, pair_t, out_off, items, n_items, top2_idx, top2_d2};
-    evz::match_top2_kernel<<<h->sm_count, evz::kThreads, evz::kMatchSmemBytes, st>>>(h->tmap, a);
+    evz::MatchArgs a{ckey, row_off, n_kp, pair_q, pair_t, out_off, items, n_items, top2_idx, top2_d2, desc, -512};
+    if (h->opt_match_variant == 1)
+        evz::match_top2_kernel<1><<<h->sm_count, evz::kThreads, evz::kMatchSmemBytes, st>>>(h->tmap, a);
+    else
+        evz::match_top2_kernel<0><<<h->sm_count, evz::kThreads, evz::kMatchSmemBytes, st>>>(h->tmap, a);
     EVZ_LAUNCH_CHECK(h);
     return EVZ_OK;
 }

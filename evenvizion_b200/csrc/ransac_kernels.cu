@@ -303,6 +303,62 @@ __device__ __forceinline__ void fused_thresholds(const float (&h)[8], float cmax
     if (D < 2.f) tlo = t - 1.25f * 6.f * D - 1e-4f;
 }
 
+// Fused scoring of NJ hypotheses per thread (slots s0 + j*kRsThreads + tid) against all matches;
+// writes the count bounds of every live slot and returns the thread's best lower bound.
+template <int NJ>
+__device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, const uint16_t* vlist,
+                                           uint16_t* lo_s, uint16_t* hi_s, int s0, int n_valid, int m, float cmax,
+                                           uint32_t pair_level) {
+    const int tid = threadIdx.x;
+    float hf[NJ][8];
+    float tlo[NJ], thi[NJ];
+    int lo[NJ], out[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int slot = s0 + j * kRsThreads + tid;
+        lo[j] = 0; out[j] = 0;
+        tlo[j] = -INFINITY; thi[j] = -INFINITY;            // idle slot: everything "sure out"
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hf[j][i] = 0.f;
+        if (slot < n_valid) {
+            int idx[4];
+            sample4(a.seed, pair_level, static_cast<uint32_t>(vlist[slot]), m, idx);
+            const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
+            double H[9];
+            solve4(q, H);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hf[j][i] = static_cast<float>(H[i]);
+            fused_thresholds(hf[j], cmax, a.thresh2, a.exact_only != 0, tlo[j], thi[j]);
+        }
+    }
+    for (int i = 0; i < m; ++i) {
+        const float4 pt = pts[i];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float den = __fmaf_rn(hf[j][6], pt.x, __fmaf_rn(hf[j][7], pt.y, 1.f));
+            float ww;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ww) : "f"(den));
+            const float X = __fmaf_rn(hf[j][0], pt.x, __fmaf_rn(hf[j][1], pt.y, hf[j][2]));
+            const float Y = __fmaf_rn(hf[j][3], pt.x, __fmaf_rn(hf[j][4], pt.y, hf[j][5]));
+            const float dx = __fmaf_rn(X, ww, -pt.z);
+            const float dy = __fmaf_rn(Y, ww, -pt.w);
+            const float e = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+            // |den| too small: not classifiable -> NaN fails both tests below (counted as unsure)
+            const float e2 = fabsf(den) >= kDenMin ? e : __int_as_float(0x7fc00000);
+            asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(lo[j]) : "f"(e2), "f"(tlo[j]));
+            asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(out[j]) : "f"(e2), "f"(thi[j]));
+        }
+    }
+    int my_lo = 0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int slot = s0 + j * kRsThreads + tid;
+        if (slot < n_valid) { lo_s[slot] = static_cast<uint16_t>(lo[j]); hi_s[slot] = static_cast<uint16_t>(m - out[j]); }
+        my_lo = max(my_lo, lo[j]);
+    }
+    return my_lo;
+}
+
 // dynamic shared memory of the scoring kernel: float4 pts[max_cnt] | u16 vlist, slist, lo_s, hi_s [n_hyp] each
 __global__ void __launch_bounds__(kRsThreads, 3)
 ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __restrict__ phase) {
@@ -399,53 +455,14 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     // ---------------- pass 1: fused scoring of the valid hypotheses with count bounds [lo, hi]
     unsigned long long best_key = 0;      // (exact count << 32) | ~hyp   of hypotheses whose count is already exact
     for (int s0 = 0; s0 < n_valid; s0 += kRsThreads * kHpt) {
-        float hf[kHpt][8];
-        float tlo[kHpt], thi[kHpt];
-        int lo[kHpt], hi[kHpt], out[kHpt];
-#pragma unroll
-        for (int j = 0; j < kHpt; ++j) {
-            const int slot = s0 + j * kRsThreads + tid;
-            lo[j] = 0; hi[j] = 0; out[j] = 0;
-            tlo[j] = -INFINITY; thi[j] = -INFINITY;            // idle slot: everything "sure out"
-#pragma unroll
-            for (int i = 0; i < 8; ++i) hf[j][i] = 0.f;
-            if (slot < n_valid) {
-                int idx[4];
-                sample4(a.seed, pair_level, static_cast<uint32_t>(vlist[slot]), m, idx);
-                const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
-                double H[9];
-                solve4(q, H);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) hf[j][i] = static_cast<float>(H[i]);
-                fused_thresholds(hf[j], cmax, a.thresh2, a.exact_only != 0, tlo[j], thi[j]);
-            }
-        }
-        for (int i = 0; i < m; ++i) {
-            const float4 pt = pts[i];
-#pragma unroll
-            for (int j = 0; j < kHpt; ++j) {
-                const float den = __fmaf_rn(hf[j][6], pt.x, __fmaf_rn(hf[j][7], pt.y, 1.f));
-                float ww;
-                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ww) : "f"(den));
-                const float X = __fmaf_rn(hf[j][0], pt.x, __fmaf_rn(hf[j][1], pt.y, hf[j][2]));
-                const float Y = __fmaf_rn(hf[j][3], pt.x, __fmaf_rn(hf[j][4], pt.y, hf[j][5]));
-                const float dx = __fmaf_rn(X, ww, -pt.z);
-                const float dy = __fmaf_rn(Y, ww, -pt.w);
-                const float e = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
-                // |den| too small: not classifiable -> NaN fails both tests below (counted as unsure)
-                const float e2 = fabsf(den) >= kDenMin ? e : __int_as_float(0x7fc00000);
-                asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(lo[j]) : "f"(e2), "f"(tlo[j]));
-                asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(out[j]) : "f"(e2), "f"(thi[j]));
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kHpt; ++j) hi[j] = m - out[j];
-        int my_lo = 0;
-#pragma unroll
-        for (int j = 0; j < kHpt; ++j) {
-            const int slot = s0 + j * kRsThreads + tid;
-            if (slot < n_valid) { lo_s[slot] = static_cast<uint16_t>(lo[j]); hi_s[slot] = static_cast<uint16_t>(hi[j]); }
-            my_lo = max(my_lo, lo[j]);
+        // live hypotheses per thread in this batch (1..kHpt): idle slots are not evaluated
+        const int nj = min(kHpt, (n_valid - s0 + kRsThreads - 1) / kRsThreads);
+        int my_lo;
+        switch (nj) {
+            case 1:  my_lo = score_batch<1>(a, pts, vlist, lo_s, hi_s, s0, n_valid, m, cmax, pair_level); break;
+            case 2:  my_lo = score_batch<2>(a, pts, vlist, lo_s, hi_s, s0, n_valid, m, cmax, pair_level); break;
+            case 3:  my_lo = score_batch<3>(a, pts, vlist, lo_s, hi_s, s0, n_valid, m, cmax, pair_level); break;
+            default: my_lo = score_batch<4>(a, pts, vlist, lo_s, hi_s, s0, n_valid, m, cmax, pair_level); break;
         }
         atomicMax(&s_lbest, my_lo);
     }

@@ -148,3 +148,29 @@ def test_match_full_size_properties(engine):
     rs = engine.match(st, [3], [3])
     o = int(st.row_off_h[3])
     assert (rs.top2_d2[o:o + 2048, 0] == 0).all()
+
+
+def test_match_epilogue_variants_agree(engine):
+    """Default epilogue (chunk minima + exact fix-up) vs the straightforward exact top-2 per element."""
+    from evenvizion_b200 import synth
+    ch = synth.make_chain(6, 2048, seed=8, device="cuda")
+    d = ch["desc"].clone()
+    d[2, 100:140] = d[2, 60:100]          # exact duplicate train rows: ties inside and across chunks
+    d[3, 8:16] = d[3, 0:8]
+    d[4, :] = d[4, 0:1]                   # a whole frame of identical descriptors
+    st = engine.ingest(d, ch["coords"])
+    outs = []
+    for v in (0, 1):
+        engine.set_option(2, v)
+        outs.append(engine.match(st, list(range(1, 6)), list(range(0, 5))))
+    engine.set_option(2, 0)
+    q0 = int(st.row_off_h[1])
+    assert torch.equal(outs[0].top2_idx[q0:], outs[1].top2_idx[q0:])
+    assert torch.equal(outs[0].top2_d2[q0:], outs[1].top2_d2[q0:])
+    # and both equal the oracle on the tie-heavy pairs
+    dn = d.cpu().numpy()
+    for p in (2, 3, 4):
+        idx, d2 = matching.knn_top2(dn[p + 1], dn[p])
+        o = int(st.row_off_h[p + 1])
+        assert np.array_equal(outs[0].top2_idx[o:o + 2048].cpu().numpy(), idx)
+        assert np.array_equal(outs[0].top2_d2[o:o + 2048].cpu().numpy().astype(np.int64), d2)

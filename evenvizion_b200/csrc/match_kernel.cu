@@ -12,23 +12,28 @@
 //   key = ckey[c] - 512 * acc = ((||t_c||^2 - 2 q.t_c) << 8) | c      (one IMAD on the FMA pipe; the
 //   multiplier is a kernel argument so that ptxas cannot strength-reduce it onto the ALU pipe)
 // ckey[c] = (||t_c||^2 << 8) | (c & 255) comes from the frame store, INT32_MAX for padding rows;
-// it is staged next to the train tile by a 1 KB bulk copy.  ||t||^2 - 2 q.t >= -||q||^2 >= -8323200,
+// it is staged by 1 KB bulk copies into its own ring.  ||t||^2 - 2 q.t >= -||q||^2 >= -8323200,
 // so the key fits in int32, and a signed min over keys is the lexicographic (distance, index)
 // minimum: ties go to the lowest train index exactly as OpenCV's batchDistance does.  ||q||^2 is
-// added once per row after the reduction.  A running top-2 per row is merged across tiles on
-// (value, frame-local index).
+// added once per row after the reduction.
 //
-// The ALU pipe (min/max) bounds the epilogue, so the default variant does not track an exact top-2
-// per element.  It reduces every aligned chunk of 8 columns to its minimum with 3-input mins
-// (4 ops / 8 elements) and keeps the two smallest CHUNK minima (3 ops / 8 elements).  The smallest
-// is the exact nearest neighbour; the second neighbour is either the other chunk minimum or one of
-// the 7 remaining columns of the winning chunk, which a per-row fix-up at the end of the item
-// recomputes exactly (u8 dp4a, query row from the swizzled smem tile, 1 KB of train rows from L2).
-// Variant 1 (EVZ_OPT_MATCH_VARIANT) is the straightforward exact top-2 per element, kept for A/B.
+// The K dimension is only 128, so the kernel is bound by the epilogue's instruction issue, not by
+// the tensor pipe: an exact running top-2 costs 2.5 min/max per element on the ALU pipe (kChunk = 0,
+// kept for A/B).  The default epilogue spends ~1 ALU op per element instead:
+//   * every aligned chunk of kChunk (8 or 16) columns is reduced to its minimum key with 3-input
+//     mins, and a running top-2 of CHUNK minima is kept per thread;
+//   * whenever a chunk minimum beats the thread's running best, the chunk's raw keys are saved to
+//     a per-thread shared-memory slot by two (four) predicated 128-bit stores, so at the end of the
+//     item the slot holds the keys of the chunk that contains the nearest neighbour;
+//   * the second neighbour is the smaller of the second-best chunk minimum and the best of the
+//     other keys in that slot -- both exact, no recomputation.
+// The running best crosses tile boundaries as a sentinel key (V1 << 8, made distinct from every
+// real key of the thread's column range), so a later tile only wins with a strictly smaller distance.
 //
-// Warp roles (384 threads, 1 CTA / SM, persistent over items):
-//   warp 0 : TMA producer        warp 1 : MMA issuer       warp 2 : TMEM allocator
-//   warps 4-11 : epilogue; warp w reads TMEM lanes 32*(w%4).. and columns 128*((w-4)/4)..
+// Warp roles (128 + 32 kEW threads, 1 CTA / SM, persistent over items):
+//   warp 0 : TMA producer (query block, train tiles, item descriptor ring)   warp 1 : MMA issuer
+//   warp 2 : TMEM allocator        warp 3 : ckey producer
+//   warps 4.. : kEW epilogue warps; warp w reads TMEM lanes 32*(w%4).. and the column group (w-4)/4
 #include "evz_common.cuh"
 #include "evz_ptx.cuh"
 #include <climits>
@@ -38,26 +43,42 @@ namespace evz {
 constexpr int kBlockQ      = 256;   // query rows per item (two 128-row MMA sub-tiles)
 constexpr int kBlockT      = 256;   // train rows per tile (MMA N)
 constexpr int kRowBytes    = 128;   // descriptor bytes = one SWIZZLE_128B row
-constexpr int kStages      = 4;     // train-tile ring depth
-constexpr int kEpiWarps    = 8;
-constexpr int kThreads     = 128 + kEpiWarps * 32;
+constexpr int kStages      = 3;     // train-tile ring depth (released by the MMA commit alone)
+constexpr int kCkStages    = 8;     // ckey-tile ring depth (released by the epilogue)
 constexpr int kTileBytes   = kBlockT * kRowBytes;   // 32 KB
 constexpr int kQBytes      = kBlockQ * kRowBytes;   // 32 KB
 constexpr int kCkeyBytes   = kBlockT * 4;           // 1 KB
 constexpr int kAbsent      = 0x7FFFFF;              // INT32_MAX >> 8: "no neighbour"
 
-struct MatchSmem {
+struct Item {
+    int q_row0, nq_left, t_row0, nt, n_tiles, n_sub, out_row0, pad;
+};
+
+// kEW epilogue warps (8 or 16); kChunk keys per save slot (8 or 16; 0 = exact per-element top-2, no slots)
+template <int kChunk, int kEW>
+struct MatchCfg {
+    static constexpr int epi_threads = kEW * 32;
+    static constexpr int threads     = 128 + epi_threads;
+    static constexpr int groups      = kEW / 4;                   // column groups of the accumulator
+    static constexpr int cols        = kBlockT / groups;          // accumulator columns per epilogue thread and tile
+    static constexpr int part_stride = epi_threads * 16;          // save slots are laid out [sub][part][thread] x 16 B
+    static constexpr int parts       = kChunk / 4;
     // offsets into dynamic shared memory (base aligned to 1024)
     static constexpr int q_off     = 0;                               // 2 x 32 KB
     static constexpr int t_off     = q_off + 2 * kQBytes;             // kStages x 32 KB
-    static constexpr int ckey_off  = t_off + kStages * kTileBytes;    // kStages x 1 KB
-    static constexpr int merge_off = ckey_off + kStages * kCkeyBytes; // 2 x 256 rows x int4
-    static constexpr int bar_off   = merge_off + 2 * 256 * 16;
-    static constexpr int n_bars    = 2 * kStages + 2 + 2 + 2 + 2;
+    static constexpr int ckey_off  = t_off + kStages * kTileBytes;    // kCkStages x 1 KB
+    static constexpr int merge_rows = (groups - 1) * 256;             // one merge buffer: (groups-1) x 256 rows x int4
+    static constexpr int merge_off = ckey_off + kCkStages * kCkeyBytes; // two buffers, alternating per item
+    static constexpr int slot_off  = merge_off + 2 * merge_rows * 16;
+    static constexpr int item_off  = slot_off + 2 * parts * part_stride;
+    static constexpr int bar_off   = item_off + 2 * static_cast<int>(sizeof(Item));
+    static constexpr int n_bars    = 2 * kStages + 2 * kCkStages + 2 + 2 + 2 + 2;
     static constexpr int tmem_off  = bar_off + n_bars * 8;
     static constexpr int total     = tmem_off + 16;
+    static constexpr int smem_bytes = total + 1024;               // + alignment slack
+    static_assert(smem_bytes <= 227 * 1024, "match kernel shared memory exceeds 227 KB");
+    static_assert(kEW == 8 || kEW == 16, "epilogue warps come in groups of four (TMEM lane quarters)");
 };
-constexpr int kMatchSmemBytes = MatchSmem::total + 1024;   // + alignment slack
 
 struct MatchArgs {
     const int32_t* ckey;
@@ -70,12 +91,7 @@ struct MatchArgs {
     const int32_t* n_items;    // device scalar
     int32_t* top2_idx;
     int32_t* top2_d2;
-    const uint8_t* desc;       // frame store descriptors (fix-up reads train rows through L2)
     int neg512;                // -512, passed at run time (see header)
-};
-
-struct Item {
-    int q_row0, nq_left, t_row0, nt, n_tiles, n_sub, out_row0;
 };
 
 __device__ __forceinline__ Item load_item(const MatchArgs& a, int it) {
@@ -90,15 +106,10 @@ __device__ __forceinline__ Item load_item(const MatchArgs& a, int it) {
     r.nt = a.n_kp[tf];
     r.n_tiles = (r.nt + kBlockT - 1) / kBlockT;
     r.out_row0 = a.out_off[p] + blk * kBlockQ;
+    r.pad = 0;
     return r;
 }
 
-// running top-2 of packed keys, two elements at a time (5 ALU ops / 2 elements)
-__device__ __forceinline__ void top2_pair(int k0, int k1, int& m1, int& m2) {
-    const int lo = min(k0, k1), hi = max(k0, k1);
-    m2 = __vimin3_s32(m2, hi, max(m1, lo));
-    m1 = min(m1, lo);
-}
 // lexicographic (value, index) insertion into a running top-2
 __device__ __forceinline__ void top2_insert(int v, int i, int& V1, int& I1, int& V2, int& I2) {
     const bool lt1 = (v < V1) || (v == V1 && i < I1);
@@ -107,131 +118,151 @@ __device__ __forceinline__ void top2_insert(int v, int i, int& V1, int& I1, int&
     else if (lt2) { V2 = v;  I2 = i; }
 }
 
-// drain one 128-column half of a 128 x 256 accumulator into a tile-local top-2 of packed keys
-__device__ __forceinline__ void drain_half(uint32_t taddr, const int32_t* ck, int& m1, int& m2) {
-    int a1 = INT_MAX, a2 = INT_MAX, b1 = INT_MAX, b2 = INT_MAX;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(taddr + c * 64, r0);
-        tmem_ld_32x32b_x32(taddr + c * 64 + 32, r1);
-        tmem_ld_wait();
-        const int4* ck4 = reinterpret_cast<const int4*>(ck + c * 64);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int4 k = ck4[j];
-            top2_pair(k.x - 512 * static_cast<int>(r0[4 * j + 0]), k.y - 512 * static_cast<int>(r0[4 * j + 1]), a1, a2);
-            top2_pair(k.z - 512 * static_cast<int>(r0[4 * j + 2]), k.w - 512 * static_cast<int>(r0[4 * j + 3]), b1, b2);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int4 k = ck4[8 + j];
-            top2_pair(k.x - 512 * static_cast<int>(r1[4 * j + 0]), k.y - 512 * static_cast<int>(r1[4 * j + 1]), a1, a2);
-            top2_pair(k.z - 512 * static_cast<int>(r1[4 * j + 2]), k.w - 512 * static_cast<int>(r1[4 * j + 3]), b1, b2);
-        }
-    }
-    m1 = min(a1, b1);
-    m2 = __vimin3_s32(max(a1, b1), a2, b2);
+// 128-bit shared-memory load through a 32-bit shared address (the dynamic smem base is realigned by
+// integer arithmetic, which hides the address space from nvcc: plain loads would become generic LD)
+__device__ __forceinline__ int4 lds128(uint32_t addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
 }
-
 __device__ __forceinline__ int mad_key(uint32_t acc, int mul, int ck) {
     int r;
     asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(static_cast<int>(acc)), "r"(mul), "r"(ck));
     return r;
 }
-// minimum packed key of 8 consecutive columns: 3 x min3 + 1 x min
-__device__ __forceinline__ int chunk_min8(const uint32_t* r, const int4 ka, const int4 kb, int mul) {
-    const int m0 = __vimin3_s32(mad_key(r[0], mul, ka.x), mad_key(r[1], mul, ka.y), mad_key(r[2], mul, ka.z));
-    const int m1 = __vimin3_s32(mad_key(r[3], mul, ka.w), mad_key(r[4], mul, kb.x), mad_key(r[5], mul, kb.y));
-    return __vimin3_s32(m0, m1, min(mad_key(r[6], mul, kb.z), mad_key(r[7], mul, kb.w)));
-}
-__device__ __forceinline__ void top2_one(int k, int& m1, int& m2) {
-    m2 = min(m2, max(m1, k));
-    m1 = min(m1, k);
-}
-// drain one 128-column half into the two smallest CHUNK minima (chunks of 8 columns)
-__device__ __forceinline__ void drain_half_chunked(uint32_t taddr, const int32_t* ck, int mul, int& m1, int& m2) {
-    int a1 = INT_MAX, a2 = INT_MAX, b1 = INT_MAX, b2 = INT_MAX;
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(taddr + c * 64, r0);
-        tmem_ld_32x32b_x32(taddr + c * 64 + 32, r1);
-        tmem_ld_wait();
-        const int4* ck4 = reinterpret_cast<const int4*>(ck + c * 64);
-#pragma unroll
-        for (int q = 0; q < 4; q += 2) {
-            top2_one(chunk_min8(r0 + 8 * q, ck4[2 * q], ck4[2 * q + 1], mul), a1, a2);
-            top2_one(chunk_min8(r0 + 8 * q + 8, ck4[2 * q + 2], ck4[2 * q + 3], mul), b1, b2);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q += 2) {
-            top2_one(chunk_min8(r1 + 8 * q, ck4[8 + 2 * q], ck4[8 + 2 * q + 1], mul), a1, a2);
-            top2_one(chunk_min8(r1 + 8 * q + 8, ck4[8 + 2 * q + 2], ck4[8 + 2 * q + 3], mul), b1, b2);
-        }
-    }
-    m1 = min(a1, b1);
-    m2 = __vimin3_s32(max(a1, b1), a2, b2);
+
+// ---- kChunk = 0: exact running top-2 of packed keys, two elements at a time (5 ALU ops / 2 elements)
+__device__ __forceinline__ void top2_pair(int k0, int k1, int& m1, int& m2) {
+    const int lo = min(k0, k1), hi = max(k0, k1);
+    m2 = __vimin3_s32(m2, hi, max(m1, lo));
+    m1 = min(m1, lo);
 }
 
-// exact second neighbour: the 7 other columns of the winning chunk against (V2, I2)
-__device__ __forceinline__ void fixup_second(const uint8_t* q_tile, int r, const uint8_t* desc, const int32_t* ckey,
-                                             int t_row0, int I1, int& V2, int& I2) {
-    const int cb = I1 & ~7;
-    const uint4* trow = reinterpret_cast<const uint4*>(desc + (static_cast<size_t>(t_row0) + cb) * kRowBytes);
-    unsigned int dot[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dot[j] = 0;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const uint4 qv = *reinterpret_cast<const uint4*>(q_tile + r * kRowBytes + ((c ^ (r & 7)) << 4));   // SWIZZLE_128B
+// ---- kChunk = 8 / 16: chunk minima + predicated save of the best chunk's keys
+template <int kStride>
+__device__ __forceinline__ void save_if_less8(int cm, int m1, uint32_t slot, const int* k) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.lt.s32 p, %0, %1;\n\t"
+                 "@p st.shared.v4.b32 [%2], {%3, %4, %5, %6};\n\t"
+                 "@p st.shared.v4.b32 [%2+%11], {%7, %8, %9, %10};\n\t}"
+                 :: "r"(cm), "r"(m1), "r"(slot), "r"(k[0]), "r"(k[1]), "r"(k[2]), "r"(k[3]),
+                    "r"(k[4]), "r"(k[5]), "r"(k[6]), "r"(k[7]), "n"(kStride));
+}
+template <int kStride>
+__device__ __forceinline__ void save_if_less16(int cm, int m1, uint32_t slot, const int* k) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.lt.s32 p, %0, %1;\n\t"
+                 "@p st.shared.v4.b32 [%2], {%3, %4, %5, %6};\n\t"
+                 "@p st.shared.v4.b32 [%2+%19], {%7, %8, %9, %10};\n\t"
+                 "@p st.shared.v4.b32 [%2+2*%19], {%11, %12, %13, %14};\n\t"
+                 "@p st.shared.v4.b32 [%2+3*%19], {%15, %16, %17, %18};\n\t}"
+                 :: "r"(cm), "r"(m1), "r"(slot), "r"(k[0]), "r"(k[1]), "r"(k[2]), "r"(k[3]),
+                    "r"(k[4]), "r"(k[5]), "r"(k[6]), "r"(k[7]), "r"(k[8]), "r"(k[9]), "r"(k[10]), "r"(k[11]),
+                    "r"(k[12]), "r"(k[13]), "r"(k[14]), "r"(k[15]), "n"(kStride));
+}
+
+// 32 accumulator columns (r) against their ckey values (ck): update the thread's running (m1, m2)
+template <int kChunk, int kEW>
+__device__ __forceinline__ void pass32(const uint32_t (&r)[32], const int4 (&ck)[8], int mul, int& m1, int& m2,
+                                       int& b1, int& b2, uint32_t slot) {
+    if (kChunk == 0) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const uint4 tv = __ldg(trow + j * 8 + c);
-            dot[j] = __dp4a(qv.x, tv.x, dot[j]); dot[j] = __dp4a(qv.y, tv.y, dot[j]);
-            dot[j] = __dp4a(qv.z, tv.z, dot[j]); dot[j] = __dp4a(qv.w, tv.w, dot[j]);
+            top2_pair(mad_key(r[4 * j + 0], mul, ck[j].x), mad_key(r[4 * j + 1], mul, ck[j].y), m1, m2);
+            top2_pair(mad_key(r[4 * j + 2], mul, ck[j].z), mad_key(r[4 * j + 3], mul, ck[j].w), b1, b2);
         }
-    }
-    const int4 k0 = __ldg(reinterpret_cast<const int4*>(ckey + t_row0 + cb));
-    const int4 k1 = __ldg(reinterpret_cast<const int4*>(ckey + t_row0 + cb) + 1);
-    const int ck[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    } else {
+        constexpr int kC = kChunk == 0 ? 8 : kChunk;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if (cb + j != I1 && ck[j] != INT_MAX) {
-            const int v = (ck[j] >> 8) - 2 * static_cast<int>(dot[j]);
-            const int idx = cb + j;
-            if (v < V2 || (v == V2 && idx < I2) || I2 < 0) { V2 = v; I2 = idx; }
+        for (int q = 0; q < 32 / kC; ++q) {
+            int k[16];
+#pragma unroll
+            for (int j = 0; j < kC / 4; ++j) {
+                const int4 c = ck[q * (kC / 4) + j];
+                k[4 * j + 0] = mad_key(r[q * kC + 4 * j + 0], mul, c.x);
+                k[4 * j + 1] = mad_key(r[q * kC + 4 * j + 1], mul, c.y);
+                k[4 * j + 2] = mad_key(r[q * kC + 4 * j + 2], mul, c.z);
+                k[4 * j + 3] = mad_key(r[q * kC + 4 * j + 3], mul, c.w);
+            }
+            int cm;
+            if (kC == 8) {
+                cm = __vimin3_s32(__vimin3_s32(k[0], k[1], k[2]), __vimin3_s32(k[3], k[4], k[5]), min(k[6], k[7]));
+                save_if_less8<MatchCfg<kC, kEW>::part_stride>(cm, m1, slot, k);
+            } else {
+                const int a = __vimin3_s32(k[0], k[1], k[2]), b = __vimin3_s32(k[3], k[4], k[5]), c = __vimin3_s32(k[6], k[7], k[8]);
+                const int d = __vimin3_s32(k[9], k[10], k[11]), e = __vimin3_s32(k[12], k[13], k[14]);
+                cm = min(__vimin3_s32(a, b, c), __vimin3_s32(d, e, k[15]));
+                save_if_less16<MatchCfg<kC, kEW>::part_stride>(cm, m1, slot, k);
+            }
+            m2 = min(m2, max(m1, cm));
+            m1 = min(m1, cm);
         }
     }
 }
 
-template <int kVariant>
-__global__ void __launch_bounds__(kThreads, 1)
+// Drain this thread's columns of one accumulator in batches of 32: the TMEM load and the eight
+// broadcast ckey loads of a batch are issued together (one exposed latency per batch, hidden by the
+// other epilogue warps of the scheduler), and the accumulator is handed back to the MMA warp as soon
+// as its last column is in registers, before the last batch is processed.
+template <int kChunk, int kEW>
+__device__ __forceinline__ void drain_acc(uint32_t taddr, uint32_t ck, int mul, int& m1, int& m2, uint32_t slot,
+                                          uint64_t* acc_empty, int lane) {
+    constexpr int kBatches = MatchCfg<kChunk, kEW>::cols / 32;
+    int b1 = INT_MAX, b2 = INT_MAX;            // kChunk = 0: second interleaved chain
+#pragma unroll
+    for (int b = 0; b < kBatches; ++b) {
+        uint32_t r[32];
+        int4 ckv[8];
+        tmem_ld_32x32b_x32(taddr + b * 32, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ckv[j] = lds128(ck + b * 128 + j * 16);
+        tmem_ld_wait_dep(r);
+        if (b == kBatches - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+        pass32<kChunk, kEW>(r, ckv, mul, m1, m2, b1, b2, slot);
+    }
+    if (kChunk == 0) {
+        const int lo = min(m1, b1);
+        m2 = __vimin3_s32(max(m1, b1), m2, b2);
+        m1 = lo;
+    }
+}
+
+template <int kChunk, int kEW>
+__global__ void __launch_bounds__(MatchCfg<kChunk, kEW>::threads, 1)
 match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args) {
+    using Cfg = MatchCfg<kChunk, kEW>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* q_s = smem + MatchSmem::q_off;
-    uint8_t* t_s = smem + MatchSmem::t_off;
-    int32_t* ckey_s = reinterpret_cast<int32_t*>(smem + MatchSmem::ckey_off);
-    int4* merge_s = reinterpret_cast<int4*>(smem + MatchSmem::merge_off);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MatchSmem::bar_off);
-    uint64_t* full = bars;                       // [kStages] train tile + ckey landed (TMA tx)
-    uint64_t* empty = full + kStages;            // [kStages] 1 MMA commit + kEpiWarps arrivals
-    uint64_t* q_full = empty + kStages;          // [2]
-    uint64_t* q_empty = q_full + 2;              // [2]
+    uint8_t* q_s = smem + Cfg::q_off;
+    uint8_t* t_s = smem + Cfg::t_off;
+    int32_t* ckey_s = reinterpret_cast<int32_t*>(smem + Cfg::ckey_off);
+    int4* merge_s = reinterpret_cast<int4*>(smem + Cfg::merge_off);
+    Item* item_s = reinterpret_cast<Item*>(smem + Cfg::item_off);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::bar_off);
+    uint64_t* full = bars;                       // [kStages] train tile landed (TMA tx)
+    uint64_t* empty = full + kStages;            // [kStages] MMA commit
+    uint64_t* ck_full = empty + kStages;         // [kCkStages] ckey tile landed
+    uint64_t* ck_empty = ck_full + kCkStages;    // [kCkStages] kEW arrivals
+    uint64_t* q_full = ck_empty + kCkStages;     // [2] query block landed + item descriptor published
+    uint64_t* q_empty = q_full + 2;              // [2] MMA commit + kEW arrivals
     uint64_t* acc_full = q_empty + 2;            // [2] accumulator ready (MMA commit)
-    uint64_t* acc_empty = acc_full + 2;          // [2] accumulator drained (kEpiWarps arrivals)
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + MatchSmem::tmem_off);
+    uint64_t* acc_empty = acc_full + 2;          // [2] accumulator drained (kEW arrivals)
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + Cfg::tmem_off);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap);
-        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1 + kEpiWarps); }
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kCkStages; ++i) { mbar_init(&ck_full[i], 1); mbar_init(&ck_empty[i], kEW); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1 + kEpiWarps);
-            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEpiWarps);
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1 + kEW);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kEW);
         }
         fence_mbar_init();
     }
@@ -251,18 +282,32 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args
             uint32_t stage = 0, sphase = 0, qi = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const Item im = load_item(args, it);
-                if (im.n_tiles == 0) continue;            // empty train frame: nothing to multiply
                 const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
                 ++qi;
                 mbar_wait(&q_empty[qb], qph ^ 1);
+                item_s[qb] = im;                           // published by the arrive below (release)
+                if (im.n_tiles == 0) { mbar_arrive(&q_full[qb]); continue; }   // empty train frame: nothing to multiply
                 mbar_arrive_expect_tx(&q_full[qb], kQBytes);
                 tma_load_2d(q_s + qb * kQBytes, &tmap, 0, im.q_row0, &q_full[qb]);
                 for (int n = 0; n < im.n_tiles; ++n) {
                     mbar_wait(&empty[stage], sphase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], kTileBytes + kCkeyBytes);
+                    mbar_arrive_expect_tx(&full[stage], kTileBytes);
                     tma_load_2d(t_s + stage * kTileBytes, &tmap, 0, im.t_row0 + n * kBlockT, &full[stage]);
-                    bulk_load_1d(ckey_s + stage * kBlockT, args.ckey + im.t_row0 + n * kBlockT, kCkeyBytes, &full[stage]);
                     if (++stage == kStages) { stage = 0; sphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------- ckey producer
+        if (lane == 0) {
+            uint32_t cs = 0, cph = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const Item im = load_item(args, it);
+                for (int n = 0; n < im.n_tiles; ++n) {
+                    mbar_wait(&ck_empty[cs], cph ^ 1);
+                    mbar_arrive_expect_tx(&ck_full[cs], kCkeyBytes);
+                    bulk_load_1d(ckey_s + cs * kBlockT, args.ckey + im.t_row0 + n * kBlockT, kCkeyBytes, &ck_full[cs]);
+                    if (++cs == kCkStages) { cs = 0; cph ^= 1; }
                 }
             }
         }
@@ -272,16 +317,15 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args
             constexpr uint32_t idesc = umma_idesc_u8(128, kBlockT);
             uint32_t stage = 0, sphase = 0, qi = 0, g = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-                const Item im = load_item(args, it);
-                if (im.n_tiles == 0) continue;            // empty train frame: nothing to multiply
                 const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
                 ++qi;
                 mbar_wait(&q_full[qb], qph);
+                const int n_tiles = item_s[qb].n_tiles, n_sub = item_s[qb].n_sub;
                 const uint32_t q_addr = smem_u32(q_s + qb * kQBytes);
-                for (int n = 0; n < im.n_tiles; ++n) {
+                for (int n = 0; n < n_tiles; ++n) {
                     mbar_wait(&full[stage], sphase);
                     const uint32_t t_addr = smem_u32(t_s + stage * kTileBytes);
-                    for (int sub = 0; sub < im.n_sub; ++sub, ++g) {
+                    for (int sub = 0; sub < n_sub; ++sub, ++g) {
                         const uint32_t acc = g & 1, aph = (g >> 1) & 1;
                         mbar_wait(&acc_empty[acc], aph ^ 1);
                         tc_fence_after();
@@ -301,93 +345,116 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------- epilogue
-        const int e = warp - 4;
+        const int et = threadIdx.x - 128;       // epilogue thread id
         const int quarter = warp & 3;           // TMEM lane quarter this warp may read
-        const int half = e >> 2;                // column half of the accumulator
+        const int cgrp = (warp - 4) >> 2;       // column group of the accumulator
+        const int colbase = cgrp * Cfg::cols;
         const int row_in_sub = quarter * 32 + lane;
-        uint32_t stage = 0, sphase = 0, g = 0, qi = 0;
-        int4* merge2_s = merge_s + 256;
+        const int sent_adj = colbase == 0 ? 1 : 0;   // sentinel distinct from every key of this column range
+        const uint32_t slot0 = smem_u32(smem + Cfg::slot_off) + et * 16;
+        const uint32_t ckey_base = smem_u32(ckey_s);
+        uint32_t cs = 0, cph = 0, g = 0, qi = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-            const Item im = load_item(args, it);
-            const uint32_t qb = qi & 1;
-            if (im.n_tiles > 0) ++qi;
-            int V1[2] = {INT_MAX, INT_MAX}, I1[2] = {-1, -1}, V2[2] = {INT_MAX, INT_MAX}, I2[2] = {-1, -1};
+            const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+            ++qi;
+            mbar_wait(&q_full[qb], qph);
+            const Item im = item_s[qb];
+            // ||q||^2 of this thread's two query rows: loaded now, needed when the item is written out
+            int qkey[2] = {0, 0};
+            if (cgrp == 0) {
+                qkey[0] = __ldg(args.ckey + im.q_row0 + row_in_sub);
+                qkey[1] = __ldg(args.ckey + im.q_row0 + 128 + row_in_sub);
+            }
+            int V1[2] = {kAbsent, kAbsent}, I1[2] = {-1, -1}, V2[2] = {kAbsent, kAbsent}, I2[2] = {-1, -1};
             for (int n = 0; n < im.n_tiles; ++n) {
-                mbar_wait(&full[stage], sphase);          // ckey tile visible to this thread
-                const int32_t* ck = ckey_s + stage * kBlockT + half * 128;
+                mbar_wait(&ck_full[cs], cph);
+                const uint32_t ck = ckey_base + (cs * kBlockT + colbase) * 4;
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
                     if (sub < im.n_sub) {
                         const uint32_t acc = g & 1, aph = (g >> 1) & 1;
                         mbar_wait(&acc_full[acc], aph);
                         tc_fence_after();
-                        int m1, m2;
-                        const uint32_t taddr = tmem_base + acc * kBlockT + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
-                        if (kVariant == 0) drain_half_chunked(taddr, ck, args.neg512, m1, m2);
-                        else               drain_half(taddr, ck, m1, m2);
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&acc_empty[acc]);
-                        if (m1 != INT_MAX) top2_insert(m1 >> 8, (m1 & 255) + n * kBlockT, V1[sub], I1[sub], V2[sub], I2[sub]);
-                        if (m2 != INT_MAX) top2_insert(m2 >> 8, (m2 & 255) + n * kBlockT, V1[sub], I1[sub], V2[sub], I2[sub]);
+                        const uint32_t taddr = tmem_base + acc * kBlockT + colbase + (static_cast<uint32_t>(quarter * 32) << 16);
+                        if (kChunk == 0) {
+                            int m1 = INT_MAX, m2 = INT_MAX;
+                            drain_acc<kChunk, kEW>(taddr, ck, args.neg512, m1, m2, 0u, &acc_empty[acc], lane);
+                            top2_insert(m1 >> 8, (m1 & 255) + n * kBlockT, V1[sub], I1[sub], V2[sub], I2[sub]);
+                            top2_insert(m2 >> 8, (m2 & 255) + n * kBlockT, V1[sub], I1[sub], V2[sub], I2[sub]);
+                        } else {
+                            // the running best enters the tile as a sentinel: a chunk only wins (and is saved)
+                            // with a strictly smaller distance
+                            const int sentinel = V1[sub] * 256 - sent_adj;
+                            int m1 = sentinel, m2 = INT_MAX;
+                            drain_acc<kChunk, kEW>(taddr, ck, args.neg512, m1, m2, slot0 + sub * (Cfg::parts * Cfg::part_stride),
+                                                   &acc_empty[acc], lane);
+                            if (m1 != sentinel) {
+                                if (m2 == sentinel) { V2[sub] = V1[sub]; I2[sub] = I1[sub]; }
+                                else                { V2[sub] = m2 >> 8; I2[sub] = (m2 & 255) + n * kBlockT; }
+                                V1[sub] = m1 >> 8; I1[sub] = (m1 & 255) + n * kBlockT;
+                            } else if ((m2 >> 8) < V2[sub]) {
+                                V2[sub] = m2 >> 8; I2[sub] = (m2 & 255) + n * kBlockT;
+                            }
+                        }
                         ++g;
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[stage]);
-                if (++stage == kStages) { stage = 0; sphase ^= 1; }
+                if (lane == 0) mbar_arrive(&ck_empty[cs]);
+                if (++cs == kCkStages) { cs = 0; cph ^= 1; }
             }
-            // merge the two column halves through shared memory
-            if (half == 1) {
-                merge_s[row_in_sub] = make_int4(V1[0], I1[0], V2[0], I2[0]);
-                merge_s[128 + row_in_sub] = make_int4(V1[1], I1[1], V2[1], I2[1]);
-            }
-            named_bar_sync(1, kEpiWarps * 32);
-            if (half == 0) {
+            if (kChunk != 0) {
+                // exact second neighbour: the other keys of the chunk that holds the nearest one
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
-                    const int4 o = merge_s[sub * 128 + row_in_sub];
-                    if (o.y >= 0) top2_insert(o.x, o.y, V1[sub], I1[sub], V2[sub], I2[sub]);
-                    if (o.w >= 0) top2_insert(o.z, o.w, V1[sub], I1[sub], V2[sub], I2[sub]);
-                    if (kVariant == 0) merge2_s[sub * 128 + row_in_sub] = make_int4(V1[sub], I1[sub], V2[sub], I2[sub]);
-                }
-            }
-            if (kVariant == 0) {
-                // second barrier: the merged candidates are visible; warps of column half h finish the rows of sub-tile h
-                named_bar_sync(1, kEpiWarps * 32);
-                const int r = half * 128 + row_in_sub;
-                if (r < im.nq_left) {
-                    const int4 o = merge2_s[r];
-                    int v1 = o.x, i1 = o.y, v2 = o.z, i2 = o.w;
-                    if (i1 >= 0) fixup_second(q_s + qb * kQBytes, r, args.desc, args.ckey, im.t_row0, i1, v2, i2);
-                    const int qn = args.ckey[im.q_row0 + r] >> 8;
-                    const int64_t o_row = static_cast<int64_t>(im.out_row0) + r;
-                    int2 oi, od;
-                    oi.x = i1; od.x = i1 >= 0 ? v1 + qn : -1;
-                    oi.y = i2; od.y = i2 >= 0 ? v2 + qn : -1;
-                    reinterpret_cast<int2*>(args.top2_idx)[o_row] = oi;
-                    reinterpret_cast<int2*>(args.top2_d2)[o_row] = od;
-                }
-            } else {
-                if (half == 0) {
+                    if (I1[sub] >= 0) {
+                        const int wkey = V1[sub] * 256 + (I1[sub] & 255);
+                        int cand = INT_MAX;
 #pragma unroll
-                    for (int sub = 0; sub < 2; ++sub) {
-                        const int r = sub * 128 + row_in_sub;
-                        if (r < im.nq_left) {
-                            const int qn = args.ckey[im.q_row0 + r] >> 8;
-                            const int64_t o_row = static_cast<int64_t>(im.out_row0) + r;
-                            int2 oi, od;
-                            oi.x = I1[sub]; od.x = I1[sub] >= 0 ? V1[sub] + qn : -1;
-                            oi.y = I2[sub]; od.y = I2[sub] >= 0 ? V2[sub] + qn : -1;
-                            reinterpret_cast<int2*>(args.top2_idx)[o_row] = oi;
-                            reinterpret_cast<int2*>(args.top2_d2)[o_row] = od;
+                        for (int part = 0; part < Cfg::parts; ++part) {
+                            const int4 k = lds128(slot0 + sub * (Cfg::parts * Cfg::part_stride) + part * Cfg::part_stride);
+                            cand = min(cand, k.x == wkey ? INT_MAX : k.x);
+                            cand = min(cand, k.y == wkey ? INT_MAX : k.y);
+                            cand = min(cand, k.z == wkey ? INT_MAX : k.z);
+                            cand = min(cand, k.w == wkey ? INT_MAX : k.w);
                         }
+                        const int v = cand >> 8, i = (I1[sub] & ~255) + (cand & 255);
+                        if (v < V2[sub] || (v == V2[sub] && i < I2[sub])) { V2[sub] = v; I2[sub] = i; }
                     }
                 }
-                named_bar_sync(1, kEpiWarps * 32);
             }
-            // the query tile in shared memory may now be overwritten (the fix-up read it)
-            if (im.n_tiles > 0) { __syncwarp(); if (lane == 0) mbar_arrive(&q_empty[qb]); }
+            // merge the column groups through shared memory: groups 1.. hand their candidates to group 0 and
+            // move on (bar.arrive); the merge buffer alternates per item, and a writer can be at most two
+            // accumulators ahead of group 0, so a buffer is never rewritten before it has been read
+            int4* mbuf = merge_s + (qi & 1) * Cfg::merge_rows;
+            if (cgrp > 0) {
+                mbuf[(cgrp - 1) * 256 + row_in_sub] = make_int4(V1[0], I1[0], V2[0], I2[0]);
+                mbuf[(cgrp - 1) * 256 + 128 + row_in_sub] = make_int4(V1[1], I1[1], V2[1], I2[1]);
+                named_bar_arrive(1, Cfg::epi_threads);
+            } else {
+                named_bar_sync(1, Cfg::epi_threads);
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+                    for (int gq = 0; gq < Cfg::groups - 1; ++gq) {
+                        const int4 o = mbuf[gq * 256 + sub * 128 + row_in_sub];
+                        if (o.y >= 0) top2_insert(o.x, o.y, V1[sub], I1[sub], V2[sub], I2[sub]);
+                        if (o.w >= 0) top2_insert(o.z, o.w, V1[sub], I1[sub], V2[sub], I2[sub]);
+                    }
+                    const int r = sub * 128 + row_in_sub;
+                    if (r < im.nq_left) {
+                        const int qn = qkey[sub] >> 8;
+                        const int64_t o_row = static_cast<int64_t>(im.out_row0) + r;
+                        int2 oi, od;
+                        oi.x = I1[sub]; od.x = I1[sub] >= 0 ? V1[sub] + qn : -1;
+                        oi.y = I2[sub]; od.y = I2[sub] >= 0 ? V2[sub] + qn : -1;
+                        reinterpret_cast<int2*>(args.top2_idx)[o_row] = oi;
+                        reinterpret_cast<int2*>(args.top2_d2)[o_row] = od;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_empty[qb]);
         }
     }
 
@@ -484,16 +551,28 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
     int32_t* items = n_items + 64;
     evz::build_items_kernel<<<1, 1024, 0, st>>>(n_kp, pair_q, n_pairs, items, n_items, static_cast<int>(capacity));
     EVZ_LAUNCH_CHECK(h);
-    if (!h->match_attr_set) {
-        EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::kMatchSmemBytes));
-        EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::kMatchSmemBytes));
-        h->match_attr_set = true;
+    evz::MatchArgs a{ckey, row_off, n_kp, pair_q, pair_t, out_off, items, n_items, top2_idx, top2_d2, -512};
+    // EVZ_OPT_MATCH_VARIANT: 0 = chunk 8 / 8 epilogue warps (default), 1 = exact per-element top-2 / 8 warps,
+    // 2 = chunk 16 / 8 warps, 3 = chunk 8 / 16 warps, 4 = exact per-element / 16 warps
+#define EVZ_MATCH_LAUNCH(CH, EW)                                                                                         \
+    do {                                                                                                                 \
+        using Cfg = evz::MatchCfg<CH, EW>;                                                                               \
+        static bool attr_set = false;                                                                                    \
+        if (!attr_set) {                                                                                                 \
+            EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_kernel<CH, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                   Cfg::smem_bytes));                                                    \
+            attr_set = true;                                                                                             \
+        }                                                                                                                \
+        evz::match_top2_kernel<CH, EW><<<h->sm_count, Cfg::threads, Cfg::smem_bytes, st>>>(h->tmap, a);                  \
+    } while (0)
+    switch (h->opt_match_variant) {
+        case 1:  EVZ_MATCH_LAUNCH(0, 8); break;
+        case 2:  EVZ_MATCH_LAUNCH(16, 8); break;
+        case 3:  EVZ_MATCH_LAUNCH(8, 16); break;
+        case 4:  EVZ_MATCH_LAUNCH(0, 16); break;
+        default: EVZ_MATCH_LAUNCH(8, 8); break;
     }
-    evz::MatchArgs a{ckey, row_off, n_kp, pair_q, pair_t, out_off, items, n_items, top2_idx, top2_d2, desc, -512};
-    if (h->opt_match_variant == 1)
-        evz::match_top2_kernel<1><<<h->sm_count, evz::kThreads, evz::kMatchSmemBytes, st>>>(h->tmap, a);
-    else
-        evz::match_top2_kernel<0><<<h->sm_count, evz::kThreads, evz::kMatchSmemBytes, st>>>(h->tmap, a);
+#undef EVZ_MATCH_LAUNCH
     EVZ_LAUNCH_CHECK(h);
     return EVZ_OK;
 }

@@ -79,7 +79,9 @@ int         evz_sm_count(const evz_handle* h);
 
 /* debugging / A-B options; results are identical for every setting, only the route differs */
 #define EVZ_OPT_RANSAC_EXACT   1  /* 1: score every hypothesis x match with the exactly-rounded formula (no fused fast path) */
-#define EVZ_OPT_MATCH_VARIANT  2  /* 0: default epilogue; 1: reference epilogue (full top-2 per element, no fix-up pass) */
+#define EVZ_OPT_MATCH_VARIANT  2  /* match epilogue: 0 default (chunk-8 minima + saved best chunk, 8 epilogue warps);
+                                     1 exact top-2 per element (8 warps); 2 chunk 16 (8 warps); 3 chunk 8 (16 warps);
+                                     4 exact top-2 per element (16 warps) */
 int         evz_set_option(evz_handle* h, int option, int value);
 
 /* ---- ingest: the step before the path.  Replaces the implicit

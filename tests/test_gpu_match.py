@@ -151,7 +151,8 @@ def test_match_full_size_properties(engine):
 
 
 def test_match_epilogue_variants_agree(engine):
-    """Default epilogue (chunk minima + exact fix-up) vs the straightforward exact top-2 per element."""
+    """Default epilogue (chunk minima + saved best chunk) vs the straightforward exact top-2 per element,
+    for every epilogue variant of EVZ_OPT_MATCH_VARIANT."""
     from evenvizion_b200 import synth
     ch = synth.make_chain(6, 2048, seed=8, device="cuda")
     d = ch["desc"].clone()
@@ -160,13 +161,14 @@ def test_match_epilogue_variants_agree(engine):
     d[4, :] = d[4, 0:1]                   # a whole frame of identical descriptors
     st = engine.ingest(d, ch["coords"])
     outs = []
-    for v in (0, 1):
+    for v in (0, 1, 2, 3, 4):
         engine.set_option(2, v)
         outs.append(engine.match(st, list(range(1, 6)), list(range(0, 5))))
     engine.set_option(2, 0)
     q0 = int(st.row_off_h[1])
-    assert torch.equal(outs[0].top2_idx[q0:], outs[1].top2_idx[q0:])
-    assert torch.equal(outs[0].top2_d2[q0:], outs[1].top2_d2[q0:])
+    for v in (1, 2, 3, 4):
+        assert torch.equal(outs[0].top2_idx[q0:], outs[v].top2_idx[q0:]), v
+        assert torch.equal(outs[0].top2_d2[q0:], outs[v].top2_d2[q0:]), v
     # and both equal the oracle on the tie-heavy pairs
     dn = d.cpu().numpy()
     for p in (2, 3, 4):

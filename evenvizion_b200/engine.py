@@ -295,15 +295,134 @@ class GeometryEngine:
         return out
 
     # ------------------------------------------------------------------ video-level driver
+    def _pairs_range(self, st: FrameStore, r: PairResults, p0: int, p1: int, n_hyp, seed, pair_id_base, ratio, thresh,
+                     min_matching_pts=4):
+        """match_static_kps + compute_homography for pairs [p0, p1) of an already allocated PairResults
+        (device pointers offset into the per-pair arrays; per-row arrays are addressed through out_off)."""
+        n = p1 - p0
+        if n <= 0:
+            return
+        lib, h, strm = self.lib, self.h, self._stream()
+        mk = st.max_kp
+        at = lambda t, k=1: C.c_void_p(t.data_ptr() + p0 * k * t.element_size())
+        self._check(lib.evz_match_top2(h, _ptr(st.desc), _ptr(st.ckey), st.rows, _ptr(st.row_off), _ptr(st.n_kp),
+                                       at(r.pair_q), at(r.pair_t), at(r.out_off), n, _ptr(r.top2_idx), _ptr(r.top2_d2), strm))
+        self._check(lib.evz_filter_matches(h, _ptr(r.top2_idx), _ptr(r.top2_d2), _ptr(st.coords), _ptr(st.canon),
+                                           _ptr(st.row_off), _ptr(st.n_kp), at(r.pair_q), at(r.pair_t), at(r.out_off), n,
+                                           mk, float(ratio), int(min_matching_pts), _ptr(r.surv), _ptr(r.m_idx), _ptr(r.m_pts),
+                                           at(r.m_cnt), at(r.n_filtered), at(r.status), strm))
+        self._check(lib.evz_find_homography(h, _ptr(r.m_pts), at(r.out_off), at(r.m_cnt), n, mk, None, int(n_hyp),
+                                            int(seed) & 0xFFFFFFFF, int(pair_id_base) + p0, 1, float(thresh), 0.0,
+                                            _lib.ST_NO_MODEL_1, at(r.status), at(r.H1, 9), _ptr(r.mask1), at(r.inl1),
+                                            at(r.best_hyp1), at(r.best_cnt1), _ptr(r.mask1_best), at(r.extra["H1_best"], 9), strm))
+        self._check(lib.evz_static_filter(h, _ptr(r.m_pts), at(r.out_off), at(r.m_cnt), n, at(r.H1, 9), at(r.status),
+                                          _ptr(r.static_pts), at(r.static_cnt), at(r.static_r), at(r.flags), None, strm))
+        self._check(lib.evz_find_homography(h, _ptr(r.static_pts), at(r.out_off), at(r.static_cnt), n, mk, None, int(n_hyp),
+                                            int(seed) & 0xFFFFFFFF, int(pair_id_base) + p0, 2, float(thresh), 0.7,
+                                            _lib.ST_NO_MODEL_2, at(r.status), at(r.H, 9), _ptr(r.mask2), at(r.inl2),
+                                            at(r.best_hyp2), at(r.best_cnt2), _ptr(r.mask2_best), at(r.extra["H2_best"], 9), strm))
+
+    def _alloc_results(self, st: FrameStore, pq, pt) -> PairResults:
+        P, rows = int(pq.numel()), st.rows
+        e, z = self._empty, lambda shape, dt: torch.zeros(shape, dtype=dt, device=self.device)
+        i32, u8, f64 = torch.int32, torch.uint8, torch.float64
+        r = PairResults(pair_q=pq, pair_t=pt, out_off=st.row_off[:-1][pq.long()].contiguous(),
+                        top2_idx=e((rows, 2), i32), top2_d2=e((rows, 2), i32), surv=e((rows,), u8), m_idx=e((rows, 2), i32),
+                        m_pts=e((rows, 4), torch.float32), m_cnt=e((P,), i32), n_filtered=e((P,), i32), status=e((P,), i32))
+        r.H1, r.H = z((P, 9), f64), z((P, 9), f64)
+        r.mask1, r.mask1_best, r.mask2, r.mask2_best = z((rows,), u8), z((rows,), u8), z((rows,), u8), z((rows,), u8)
+        r.inl1, r.inl2, r.best_cnt1, r.best_cnt2 = z((P,), i32), z((P,), i32), z((P,), i32), z((P,), i32)
+        r.best_hyp1 = torch.full((P,), -1, dtype=i32, device=self.device)
+        r.best_hyp2 = torch.full((P,), -1, dtype=i32, device=self.device)
+        r.extra["H1_best"], r.extra["H2_best"] = z((P, 9), f64), z((P, 9), f64)
+        r.static_pts, r.static_cnt = e((rows, 4), torch.float32), e((P,), i32)
+        r.static_r, r.flags = e((P,), i32), e((P,), i32)
+        return r
+
     def video_geometry(self, desc, coords, n_kp=None, n_hyp=1024, seed=0, none_h_processing=True,
-                       ratio=0.5, thresh=3.0, pair_id_base=0):
+                       ratio=0.5, thresh=3.0, pair_id_base=0, chunk_frames=None):
         """Frame chain -> per-pair G, status, cumulative S and fixed-plane H (parallel formulation).
-        Host arrays in, host arrays out: this is the call bench.py times end to end."""
-        st = self.ingest(desc, coords, n_kp)
-        F = st.n_frames
-        pq = torch.arange(1, F, dtype=torch.int32)
-        pt = torch.arange(0, F - 1, dtype=torch.int32)
-        r = self.process_pairs(st, pq, pt, n_hyp, seed, pair_id_base, ratio, thresh)
+        Host arrays in, host arrays out: this is the call bench.py times end to end.
+
+        Host input is streamed: frames are copied to the device in chunks on a copy stream while the
+        compute stream ingests and processes the pairs of the chunks that have already landed, so the
+        PCIe transfer (the end-to-end bound: 136 bytes per keypoint) overlaps the kernels."""
+        desc_t, coords_t = torch.as_tensor(desc), torch.as_tensor(coords)
+        if desc_t.dim() == 3:
+            f, n, d = desc_t.shape
+            if n_kp is None:
+                n_kp = np.full(f, n, np.int64)
+            desc_t, coords_t = desc_t.reshape(f * n, d), coords_t.reshape(f * n, 2)
+        if n_kp is None:
+            raise ValueError("n_kp is required for concatenated input")
+        n_kp_h = np.asarray(n_kp, np.int64)
+        F = len(n_kp_h)
+        if chunk_frames is None:
+            chunk_frames = max(64, -(-F // 16))
+        if desc_t.is_cuda or F <= chunk_frames or desc_t.dtype not in (torch.uint8, torch.float32):
+            # small or device-resident input: one ingest, one batch
+            st = self.ingest(desc_t, coords_t, n_kp_h)
+            pq = torch.arange(1, F, dtype=torch.int32)
+            pt = torch.arange(0, F - 1, dtype=torch.int32)
+            r = self.process_pairs(st, pq, pt, n_hyp, seed, pair_id_base, ratio, thresh)
+        else:
+            st, r = self._video_streamed(desc_t, coords_t, n_kp_h, chunk_frames, n_hyp, seed, pair_id_base, ratio, thresh)
         S, Hf, _ = self.chain_scan(r.H, r.status, none_h_processing)
         return dict(G=r.H.cpu().numpy().reshape(-1, 3, 3), status=r.status.cpu().numpy(),
                     S=S.cpu().numpy().reshape(-1, 3, 3), H_fixed=Hf.cpu().numpy().reshape(-1, 3, 3), results=r, store=st)
+
+    def _video_streamed(self, desc_t, coords_t, n_kp_h, chunk_frames, n_hyp, seed, pair_id_base, ratio, thresh):
+        if int(n_kp_h.sum()) != desc_t.shape[0] or coords_t.shape[0] != desc_t.shape[0]:
+            raise ValueError("n_kp does not add up to the number of descriptor rows")
+        if int(n_kp_h.max()) > EVZ_MAX_KP:
+            raise ValueError(f"at most {EVZ_MAX_KP} keypoints per frame are supported")
+        d = int(desc_t.shape[1])
+        if d > EVZ_DESC_BYTES or d % 4:
+            raise ValueError("descriptor width must be a multiple of 4 and at most 128")
+        is_f32 = 1 if desc_t.dtype == torch.float32 else 0
+        coords_t = coords_t.to(torch.float32)
+        F = len(n_kp_h)
+        dev = self.device
+        row_off_h = self.layout(n_kp_h)
+        raw_off_h = np.zeros(F + 1, np.int64)
+        np.cumsum(n_kp_h, out=raw_off_h[1:])
+        rows = int(row_off_h[-1])
+        compute = torch.cuda.current_stream(dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        copy = self._copy_stream
+        raw_off = torch.from_numpy(raw_off_h).to(dev, non_blocking=True)
+        row_off = torch.from_numpy(row_off_h).to(dev, non_blocking=True)
+        n_kp_d = torch.from_numpy(n_kp_h.astype(np.int32)).to(dev, non_blocking=True)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        desc_raw = torch.empty(desc_t.shape, dtype=desc_t.dtype, device=dev)
+        coords_raw = torch.empty(coords_t.shape, dtype=torch.float32, device=dev)
+        st = FrameStore(desc=self._empty((rows, EVZ_DESC_BYTES), torch.uint8), ckey=self._empty((rows,), torch.int32),
+                        coords=self._empty((rows, 2), torch.float32), canon=self._empty((rows,), torch.int32),
+                        row_off=row_off, n_kp=n_kp_d, row_off_h=row_off_h, n_kp_h=n_kp_h.astype(np.int32), d=d,
+                        keep=(desc_raw, coords_raw, raw_off, bad))
+        pq = torch.arange(1, F, dtype=torch.int32, device=dev)
+        pt = torch.arange(0, F - 1, dtype=torch.int32, device=dev)
+        r = self._alloc_results(st, pq, pt)
+        copy.wait_stream(compute)            # the staging buffers were allocated on the compute stream
+        off8 = lambda t, k: C.c_void_p(t.data_ptr() + k * t.element_size())
+        for f0 in range(0, F, chunk_frames):
+            f1 = min(F, f0 + chunk_frames)
+            a, b = int(raw_off_h[f0]), int(raw_off_h[f1])
+            with torch.cuda.stream(copy):
+                if b > a:
+                    desc_raw[a:b].copy_(desc_t[a:b], non_blocking=True)
+                    coords_raw[a:b].copy_(coords_t[a:b], non_blocking=True)
+                landed = copy.record_event()
+            compute.wait_event(landed)
+            if row_off_h[f1] > row_off_h[f0]:
+                self._check(self.lib.evz_ingest(self.h, _ptr(desc_raw), is_f32, d, _ptr(coords_raw), off8(raw_off, f0),
+                                                off8(row_off, f0), f1 - f0, _ptr(st.desc), _ptr(st.ckey), _ptr(st.coords),
+                                                _ptr(st.canon), _ptr(bad), self._stream()))
+            # pairs whose query frame is in this chunk (their train frame landed with this or an earlier chunk)
+            self._pairs_range(st, r, max(f0, 1) - 1, f1 - 1, n_hyp, seed, pair_id_base, ratio, thresh)
+        desc_raw.record_stream(copy); coords_raw.record_stream(copy)
+        if is_f32 and int(bad.item()):
+            raise ValueError(f"{int(bad.item())} descriptor values are not integers in [0,255]; "
+                             "the int8 tensor-core matcher is exact only for SIFT/ORB-style descriptors")
+        return st, r

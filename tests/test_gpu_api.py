@@ -131,3 +131,28 @@ def test_multi_feature_concat_dedup(proc, golden, engine):
     out = _dedup_concat([t(a1, b1), t(a2, b2)]).cpu().numpy()
     na, nb, _, _ = matching.remove_double_matching(np.r_[a1, a2], np.r_[b1, b2])
     assert np.array_equal(out[:, :2], na) and np.array_equal(out[:, 2:], nb)
+
+
+def test_video_geometry_streamed_equals_single_batch(engine):
+    """Chunked H2D/compute overlap (host input) must give bit-identical results to one batch, for
+    ragged frames, empty frames and chunk sizes that do not divide the frame count."""
+    import torch
+    from evenvizion_b200 import synth
+    ch = synth.make_chain(23, 700, seed=11, device="cpu", unmatched_frac=0.1)
+    counts = [700] * 23
+    counts[5], counts[9], counts[17] = 300, 0, 513
+    desc = torch.cat([ch["desc"][f, :n] for f, n in enumerate(counts)])
+    coords = torch.cat([ch["coords"][f, :n] for f, n in enumerate(counts)])
+    ref = engine.video_geometry(desc.cuda(), coords.cuda(), counts, n_hyp=256, seed=5, pair_id_base=40)   # single batch
+    for chunk in (4, 7, 22):
+        out = engine.video_geometry(desc.pin_memory(), coords.pin_memory(), counts, n_hyp=256, seed=5, pair_id_base=40,
+                                    chunk_frames=chunk)
+        for k in ("status", "G", "S", "H_fixed"):
+            assert np.array_equal(out[k], ref[k]), (chunk, k)
+        a, b = out["results"], ref["results"]
+        ro = out["store"].row_off_h
+        valid = np.concatenate([np.arange(ro[f], ro[f] + counts[f]) for f in range(1, 23)])     # written rows only
+        valid = torch.from_numpy(valid).cuda()
+        assert torch.equal(a.top2_idx[valid], b.top2_idx[valid]) and torch.equal(a.top2_d2[valid], b.top2_d2[valid])
+        assert torch.equal(a.m_cnt, b.m_cnt)
+        assert torch.equal(a.static_cnt, b.static_cnt) and torch.equal(a.best_hyp2, b.best_hyp2)

@@ -121,7 +121,7 @@ def run_reference(args, cfg):
     import torch
     from evenvizion_b200 import synth
     cores = os.cpu_count() or 1
-    sample_pairs = min(16 * cores, 1024)
+    sample_pairs = min(48 * cores, 1024)
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     ch = synth.make_chain(sample_pairs + 1, cfg["n_kp"], seed=0, device=dev, outlier_frac=cfg["outlier_frac"],
                           unmatched_frac=cfg["unmatched_frac"])
@@ -274,7 +274,7 @@ def run_ours(args, cfg):
         # bounded CPU baseline on the same workload (first pairs of this rank's chain)
         cpu = None
         if world == 1 and not args.no_cpu:
-            sp_pairs = min(8 * cores, 512, P)
+            sp_pairs = min(128 * cores, 2048, P)      # about 10 s of CPU work on the box's cores
             frames = [(coords_h[i].numpy(), desc_h[i].numpy()) for i in range(sp_pairs + 1)]
             sec, n, ok = cpu_reference_run(frames, cores, 1, 0)
             cpu = {"value": n / sec, "unit": "pairs/s", "cores": cores, "kind": "port",

@@ -139,26 +139,34 @@ __device__ __forceinline__ void top2_pair(int k0, int k1, int& m1, int& m2) {
 }
 
 // ---- kChunk = 8 / 16: chunk minima + predicated save of the best chunk's keys
+// returns min(cm, m1); when cm < m1 the chunk's keys go to the slot (setp + selp fuse into one
+// VIMNMX with a predicate output)
 template <int kStride>
-__device__ __forceinline__ void save_if_less8(int cm, int m1, uint32_t slot, const int* k) {
+__device__ __forceinline__ int save_if_less8(int cm, int m1, uint32_t slot, const int* k) {
+    int mn;
     asm volatile("{\n\t.reg .pred p;\n\t"
-                 "setp.lt.s32 p, %0, %1;\n\t"
-                 "@p st.shared.v4.b32 [%2], {%3, %4, %5, %6};\n\t"
-                 "@p st.shared.v4.b32 [%2+%11], {%7, %8, %9, %10};\n\t}"
-                 :: "r"(cm), "r"(m1), "r"(slot), "r"(k[0]), "r"(k[1]), "r"(k[2]), "r"(k[3]),
+                 "setp.lt.s32 p, %1, %2;\n\t"
+                 "selp.s32 %0, %1, %2, p;\n\t"
+                 "@p st.shared.v4.b32 [%3], {%4, %5, %6, %7};\n\t"
+                 "@p st.shared.v4.b32 [%3+%12], {%8, %9, %10, %11};\n\t}"
+                 : "=r"(mn) : "r"(cm), "r"(m1), "r"(slot), "r"(k[0]), "r"(k[1]), "r"(k[2]), "r"(k[3]),
                     "r"(k[4]), "r"(k[5]), "r"(k[6]), "r"(k[7]), "n"(kStride));
+    return mn;
 }
 template <int kStride>
-__device__ __forceinline__ void save_if_less16(int cm, int m1, uint32_t slot, const int* k) {
+__device__ __forceinline__ int save_if_less16(int cm, int m1, uint32_t slot, const int* k) {
+    int mn;
     asm volatile("{\n\t.reg .pred p;\n\t"
-                 "setp.lt.s32 p, %0, %1;\n\t"
-                 "@p st.shared.v4.b32 [%2], {%3, %4, %5, %6};\n\t"
-                 "@p st.shared.v4.b32 [%2+%19], {%7, %8, %9, %10};\n\t"
-                 "@p st.shared.v4.b32 [%2+2*%19], {%11, %12, %13, %14};\n\t"
-                 "@p st.shared.v4.b32 [%2+3*%19], {%15, %16, %17, %18};\n\t}"
-                 :: "r"(cm), "r"(m1), "r"(slot), "r"(k[0]), "r"(k[1]), "r"(k[2]), "r"(k[3]),
+                 "setp.lt.s32 p, %1, %2;\n\t"
+                 "selp.s32 %0, %1, %2, p;\n\t"
+                 "@p st.shared.v4.b32 [%3], {%4, %5, %6, %7};\n\t"
+                 "@p st.shared.v4.b32 [%3+%20], {%8, %9, %10, %11};\n\t"
+                 "@p st.shared.v4.b32 [%3+2*%20], {%12, %13, %14, %15};\n\t"
+                 "@p st.shared.v4.b32 [%3+3*%20], {%16, %17, %18, %19};\n\t}"
+                 : "=r"(mn) : "r"(cm), "r"(m1), "r"(slot), "r"(k[0]), "r"(k[1]), "r"(k[2]), "r"(k[3]),
                     "r"(k[4]), "r"(k[5]), "r"(k[6]), "r"(k[7]), "r"(k[8]), "r"(k[9]), "r"(k[10]), "r"(k[11]),
                     "r"(k[12]), "r"(k[13]), "r"(k[14]), "r"(k[15]), "n"(kStride));
+    return mn;
 }
 
 // 32 accumulator columns (r) against their ckey values (ck): update the thread's running (m1, m2)
@@ -184,18 +192,18 @@ __device__ __forceinline__ void pass32(const uint32_t (&r)[32], const int4 (&ck)
                 k[4 * j + 2] = mad_key(r[q * kC + 4 * j + 2], mul, c.z);
                 k[4 * j + 3] = mad_key(r[q * kC + 4 * j + 3], mul, c.w);
             }
-            int cm;
+            int cm, mn;
             if (kC == 8) {
                 cm = __vimin3_s32(__vimin3_s32(k[0], k[1], k[2]), __vimin3_s32(k[3], k[4], k[5]), min(k[6], k[7]));
-                save_if_less8<MatchCfg<kC, kEW>::part_stride>(cm, m1, slot, k);
+                mn = save_if_less8<MatchCfg<kC, kEW>::part_stride>(cm, m1, slot, k);
             } else {
                 const int a = __vimin3_s32(k[0], k[1], k[2]), b = __vimin3_s32(k[3], k[4], k[5]), c = __vimin3_s32(k[6], k[7], k[8]);
                 const int d = __vimin3_s32(k[9], k[10], k[11]), e = __vimin3_s32(k[12], k[13], k[14]);
                 cm = min(__vimin3_s32(a, b, c), __vimin3_s32(d, e, k[15]));
-                save_if_less16<MatchCfg<kC, kEW>::part_stride>(cm, m1, slot, k);
+                mn = save_if_less16<MatchCfg<kC, kEW>::part_stride>(cm, m1, slot, k);
             }
             m2 = min(m2, max(m1, cm));
-            m1 = min(m1, cm);
+            m1 = mn;
         }
     }
 }

@@ -373,7 +373,9 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args
                 qkey[0] = __ldg(args.ckey + im.q_row0 + row_in_sub);
                 qkey[1] = __ldg(args.ckey + im.q_row0 + 128 + row_in_sub);
             }
-            int V1[2] = {kAbsent, kAbsent}, I1[2] = {-1, -1}, V2[2] = {kAbsent, kAbsent}, I2[2] = {-1, -1};
+            // running best / second best of this thread's column range as packed keys (distance << 8 | column
+            // within the tile) plus the tile they came from; decoded once per item
+            int B1[2] = {kAbsent * 256, kAbsent * 256}, T1[2] = {-1, -1}, B2[2] = {INT_MAX, INT_MAX}, T2[2] = {-1, -1};
             for (int n = 0; n < im.n_tiles; ++n) {
                 mbar_wait(&ck_full[cs], cph);
                 const uint32_t ck = ckey_base + (cs * kBlockT + colbase) * 4;
@@ -387,21 +389,26 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args
                         if (kChunk == 0) {
                             int m1 = INT_MAX, m2 = INT_MAX;
                             drain_acc<kChunk, kEW>(taddr, ck, args.neg512, m1, m2, 0u, &acc_empty[acc], lane);
-                            top2_insert(m1 >> 8, (m1 & 255) + n * kBlockT, V1[sub], I1[sub], V2[sub], I2[sub]);
-                            top2_insert(m2 >> 8, (m2 & 255) + n * kBlockT, V1[sub], I1[sub], V2[sub], I2[sub]);
+                            // a later tile only displaces an earlier one with a strictly smaller distance
+#pragma unroll
+                            for (int w = 0; w < 2; ++w) {
+                                const int k = w ? m2 : m1;
+                                if ((k >> 8) < (B1[sub] >> 8))      { B2[sub] = B1[sub]; T2[sub] = T1[sub]; B1[sub] = k; T1[sub] = n; }
+                                else if ((k >> 8) < (B2[sub] >> 8)) { B2[sub] = k; T2[sub] = n; }
+                            }
                         } else {
                             // the running best enters the tile as a sentinel: a chunk only wins (and is saved)
                             // with a strictly smaller distance
-                            const int sentinel = V1[sub] * 256 - sent_adj;
+                            const int sentinel = (B1[sub] & ~255) - sent_adj;
                             int m1 = sentinel, m2 = INT_MAX;
                             drain_acc<kChunk, kEW>(taddr, ck, args.neg512, m1, m2, slot0 + sub * (Cfg::parts * Cfg::part_stride),
                                                    &acc_empty[acc], lane);
                             if (m1 != sentinel) {
-                                if (m2 == sentinel) { V2[sub] = V1[sub]; I2[sub] = I1[sub]; }
-                                else                { V2[sub] = m2 >> 8; I2[sub] = (m2 & 255) + n * kBlockT; }
-                                V1[sub] = m1 >> 8; I1[sub] = (m1 & 255) + n * kBlockT;
-                            } else if ((m2 >> 8) < V2[sub]) {
-                                V2[sub] = m2 >> 8; I2[sub] = (m2 & 255) + n * kBlockT;
+                                const bool demote = m2 == sentinel;      // the old best is the new second best
+                                B2[sub] = demote ? B1[sub] : m2; T2[sub] = demote ? T1[sub] : n;
+                                B1[sub] = m1; T1[sub] = n;
+                            } else if (m2 < (B2[sub] & ~255)) {
+                                B2[sub] = m2; T2[sub] = n;
                             }
                         }
                         ++g;
@@ -411,12 +418,18 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args
                 if (lane == 0) mbar_arrive(&ck_empty[cs]);
                 if (++cs == kCkStages) { cs = 0; cph ^= 1; }
             }
+            int V1[2], I1[2], V2[2], I2[2];
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+                V1[sub] = T1[sub] >= 0 ? B1[sub] >> 8 : kAbsent; I1[sub] = T1[sub] >= 0 ? T1[sub] * kBlockT + (B1[sub] & 255) : -1;
+                V2[sub] = T2[sub] >= 0 ? B2[sub] >> 8 : kAbsent; I2[sub] = T2[sub] >= 0 ? T2[sub] * kBlockT + (B2[sub] & 255) : -1;
+            }
             if (kChunk != 0) {
                 // exact second neighbour: the other keys of the chunk that holds the nearest one
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
                     if (I1[sub] >= 0) {
-                        const int wkey = V1[sub] * 256 + (I1[sub] & 255);
+                        const int wkey = B1[sub];
                         int cand = INT_MAX;
 #pragma unroll
                         for (int part = 0; part < Cfg::parts; ++part) {

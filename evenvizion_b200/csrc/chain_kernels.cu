@@ -205,15 +205,36 @@ prod_local_kernel(const double* __restrict__ G, const int32_t* __restrict__ src,
     if (k < n) m3_store(S + static_cast<size_t>(k) * 9, v);
     if (threadIdx.x == kScanBlock - 1) m3_store(block_tot + static_cast<size_t>(blockIdx.x) * 9, v);
 }
-// phase B2 (single CTA, sequential over blocks): exclusive prefix of block totals, seeded
-__global__ void prod_carry_kernel(const double* __restrict__ block_tot, int nb, const double* __restrict__ seed_S,
-                                  double* __restrict__ block_pre) {
-    if (threadIdx.x == 0) {
-        M3 c = seed_S ? m3_load(seed_S) : m3_identity();
-        for (int b = 0; b < nb; ++b) {
-            m3_store(block_pre + static_cast<size_t>(b) * 9, c);
-            c = m3_mul_norm(c, m3_load(block_tot + static_cast<size_t>(b) * 9));
+// phase B2 (single CTA): exclusive prefix of the block totals, seeded.  Block-wide shuffle scan over
+// chunks of kScanBlock totals (a serial loop over blocks costs ~1 us per block: L2 latency + f64 divides)
+__global__ void __launch_bounds__(kScanBlock)
+prod_carry_kernel(const double* __restrict__ block_tot, int nb, const double* __restrict__ seed_S,
+                  double* __restrict__ block_pre) {
+    __shared__ double wt[kScanBlock / 32][9];
+    __shared__ double carry_s[9];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    M3 carry = seed_S ? m3_load(seed_S) : m3_identity();
+    for (int b0 = 0; b0 < nb; b0 += kScanBlock) {
+        const int b = b0 + threadIdx.x;
+        M3 v = b < nb ? m3_load(block_tot + static_cast<size_t>(b) * 9) : m3_identity();
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const M3 t = m3_shfl_up(v, d);
+            if (lane >= d) v = m3_mul_norm(t, v);
         }
+        if (lane == 31) m3_store(wt[warp], v);
+        __syncthreads();
+        M3 c = carry;
+        for (int w = 0; w < warp; ++w) c = m3_mul_norm(c, m3_load(wt[w]));
+        const M3 incl = m3_mul_norm(c, v);                       // inclusive prefix through block b
+        // exclusive prefix = inclusive prefix of the previous block
+        M3 excl = m3_shfl_up(incl, 1);
+        if (lane == 0) excl = c;
+        if (b < nb) m3_store(block_pre + static_cast<size_t>(b) * 9, excl);
+        if (threadIdx.x == kScanBlock - 1) m3_store(carry_s, incl);
+        __syncthreads();
+        carry = m3_load(carry_s);
+        __syncthreads();
     }
 }
 // phase B3: S[k] = block_pre[b] . S_local[k]
@@ -356,7 +377,7 @@ extern "C" int evz_chain_scan(evz_handle* h, const double* G, const int32_t* sta
         // unseeded pass: leading invalid pairs are identity steps, so the total is R
         evz::prod_local_kernel<<<nb, evz::kScanBlock, 0, st>>>(G, src, n_pairs, policy, nullptr, S_work, block_tot);
         EVZ_LAUNCH_CHECK(h);
-        evz::prod_carry_kernel<<<1, 32, 0, st>>>(block_tot, nb, nullptr, block_pre);
+        evz::prod_carry_kernel<<<1, evz::kScanBlock, 0, st>>>(block_tot, nb, nullptr, block_pre);
         EVZ_LAUNCH_CHECK(h);
         evz::prod_apply_kernel<<<nb, evz::kScanBlock, 0, st>>>(S_work, block_pre, n_pairs, 0);
         EVZ_LAUNCH_CHECK(h);
@@ -366,7 +387,7 @@ extern "C" int evz_chain_scan(evz_handle* h, const double* G, const int32_t* sta
     if (S) {
         evz::prod_local_kernel<<<nb, evz::kScanBlock, 0, st>>>(G, src, n_pairs, policy, seed_G, S, block_tot);
         EVZ_LAUNCH_CHECK(h);
-        evz::prod_carry_kernel<<<1, 32, 0, st>>>(block_tot, nb, seed_S, block_pre);
+        evz::prod_carry_kernel<<<1, evz::kScanBlock, 0, st>>>(block_tot, nb, seed_S, block_pre);
         EVZ_LAUNCH_CHECK(h);
         evz::prod_apply_kernel<<<nb, evz::kScanBlock, 0, st>>>(S, block_pre, n_pairs, seed_S ? 1 : 0);
         EVZ_LAUNCH_CHECK(h);

@@ -215,22 +215,29 @@ __device__ __forceinline__ void pass32(const uint32_t (&r)[32], const int4 (&ck)
 template <int kChunk, int kEW>
 __device__ __forceinline__ void drain_acc(uint32_t taddr, uint32_t ck, int mul, int& m1, int& m2, uint32_t slot,
                                           uint64_t* acc_empty, int lane) {
-    constexpr int kBatches = MatchCfg<kChunk, kEW>::cols / 32;
+    constexpr int kCols = MatchCfg<kChunk, kEW>::cols;
+    constexpr int kBW = (kEW == 8 && kChunk != 0) ? 64 : 32;   // columns per batch: fewer, longer batches expose fewer load latencies
+    constexpr int kBatches = kCols / kBW;
     int b1 = INT_MAX, b2 = INT_MAX;            // kChunk = 0: second interleaved chain
 #pragma unroll
     for (int b = 0; b < kBatches; ++b) {
-        uint32_t r[32];
-        int4 ckv[8];
-        tmem_ld_32x32b_x32(taddr + b * 32, r);
+        uint32_t r[kBW / 32][32];
+        int4 ckv[kBW / 32][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ckv[j] = lds128(ck + b * 128 + j * 16);
-        tmem_ld_wait_dep(r);
+        for (int h = 0; h < kBW / 32; ++h) tmem_ld_32x32b_x32(taddr + b * kBW + h * 32, r[h]);
+#pragma unroll
+        for (int h = 0; h < kBW / 32; ++h)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ckv[h][j] = lds128(ck + (b * kBW + h * 32) * 4 + j * 16);
+#pragma unroll
+        for (int h = 0; h < kBW / 32; ++h) tmem_ld_wait_dep(r[h]);
         if (b == kBatches - 1) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);
         }
-        pass32<kChunk, kEW>(r, ckv, mul, m1, m2, b1, b2, slot);
+#pragma unroll
+        for (int h = 0; h < kBW / 32; ++h) pass32<kChunk, kEW>(r[h], ckv[h], mul, m1, m2, b1, b2, slot);
     }
     if (kChunk == 0) {
         const int lo = min(m1, b1);

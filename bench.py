@@ -34,7 +34,11 @@ CONFIGS = {
     4: dict(name="sharp motion: 20% inlier ratio, 4096 hypotheses/pair, none_H_processing=True", n_kp=2048, pairs=10000,
             n_hyp=4096, outlier_frac=0.8, unmatched_frac=0.02),
 }
-KERNELS_PER_STEP = 2 + 1 + 1 + 1 + 1 + 7      # build_items+match, filter, fh1, static, fh2, scan (7 kernels)
+KERNELS_PER_STEP = 2 + 1 + 2 + 1 + 2 + 7      # build_items+match, filter, score+refit, static, score+refit, scan (7 kernels)
+KERNELS_PER_STEP_MULTI = 2 + 1 + 2 + 1 + 2 + 7 + 7   # + the summary pass of the cross-GPU scan (fill x3, prod x3, summary)
+# dram__bytes_read.sum + dram__bytes_write.sum of one match_top2_kernel launch at config 2 x 10 000 pairs, from the
+# ncu --set full capture profiles/r01b_prof_match_raw.csv (algorithmic: 10 001 frames x 2048 x 132 B in + 10 000 x 2048 x 16 B out)
+MATCH_TRAFFIC_BYTES = {(2, 10000): 2704739000 + 325305856}
 
 
 def peaks():
@@ -291,14 +295,16 @@ def run_ours(args, cfg):
             "stage_ms": {"match": m_ms, "ransac_static_ransac": float(np.mean(ransac_ms)),
                          "scan": ms_per_step - m_ms - float(np.mean(ransac_ms))},
             "roofline": {"kernel": "match_top2_kernel", "bound": "tensor", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": MATCH_TRAFFIC_BYTES.get((args.config, P)),
+                         "algorithmic_bytes": (P + 1) * N * 132 + P * N * 16,
                          "peak_source": "torch._int_mm 8192^3 measured in this run (dense int8 cuBLASLt)" if i8 else "2 x MEASURED bf16 burst",
                          "peak_nominal_int8": 4500.0, "frac_of_nominal": achieved / 4500.0,
+                         "peak_2x_measured_bf16": 2.0 * pk["bf16_burst"], "frac_of_2x_measured_bf16": achieved / (2.0 * pk["bf16_burst"]),
                          "ops_per_launch": ops, "note": "ops = 2*Nq*Nt*128 per pair (int8 MAC = 2 ops)"},
             "cpu_baseline": cpu,
             "e2e": {"value": world * P / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
-            "gpu_launches": KERNELS_PER_STEP * args.steps + (6 if world > 1 else 0) * args.steps,
+            "gpu_launches": (KERNELS_PER_STEP_MULTI if world > 1 else KERNELS_PER_STEP) * args.steps,
             "clocks": clocks, "peaks": pk,
         }))
     if world > 1:

@@ -284,6 +284,14 @@ __device__ __forceinline__ float reproj_err_fused(const float (&h)[8], const flo
 //   err_fused <= t - 6D            (D < 2)    =>  err_exact <= t      (tlo, margin x1.25 + 1e-4)
 // Everything else (inside the band, |den| small, NaN) is "unsure" and counted in hi only.
 constexpr float kDenMin = 0.0625f;
+// true when |den| >= kDenMin is guaranteed on both the fused and the exact path for every point with
+// |x|, |y| <= cmax: den >= 1 - (|h6|+|h7|) cmax - 8 u Bd (same bound as dm in fused_thresholds)
+__device__ __forceinline__ bool den_safe(float h6, float h7, float cmax) {
+    const float u = 5.9604645e-8f;
+    const float a6 = fabsf(h6) + fabsf(h7);
+    const float Bd = a6 * cmax + 1.f;
+    return (8.f * u * Bd <= 0.1f * kDenMin) && ((1.f - a6 * cmax - 8.f * u * Bd) * 0.999999f >= kDenMin);
+}
 __device__ __forceinline__ void fused_thresholds(const float (&h)[8], float cmax, float t, bool exact_only,
                                                  float& tlo, float& thi) {
     const float u = 5.9604645e-8f;
@@ -305,7 +313,9 @@ __device__ __forceinline__ void fused_thresholds(const float (&h)[8], float cmax
 
 // Fused scoring of NJ hypotheses per thread (slots s0 + j*kRsThreads + tid) against all matches;
 // writes the count bounds of every live slot and returns the thread's best lower bound.
-template <int NJ>
+// kCheckDen = false is used for hypotheses whose denominator provably stays >= kDenMin over the data range
+// (den_safe below), for which the per-evaluation |den| test can never fire.
+template <int NJ, bool kCheckDen>
 __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, const uint16_t* vlist,
                                            uint16_t* lo_s, uint16_t* hi_s, int s0, int n_valid, int m, float cmax,
                                            uint32_t pair_level) {
@@ -344,7 +354,7 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
             const float dy = __fmaf_rn(Y, ww, -pt.w);
             const float e = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
             // |den| too small: not classifiable -> NaN fails both tests below (counted as unsure)
-            const float e2 = fabsf(den) >= kDenMin ? e : __int_as_float(0x7fc00000);
+            const float e2 = (!kCheckDen || fabsf(den) >= kDenMin) ? e : __int_as_float(0x7fc00000);
             asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(lo[j]) : "f"(e2), "f"(tlo[j]));
             asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(out[j]) : "f"(e2), "f"(thi[j]));
         }
@@ -370,8 +380,8 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     uint16_t* hi_s = lo_s + a.n_hyp;
     __shared__ unsigned long long red[kRsThreads / 32];
     __shared__ float cmax_s[kRsThreads / 32];
-    __shared__ int warp_sums[32];
-    __shared__ int s_flag, s_nvalid, s_nsurv, s_lbest;
+    __shared__ int warp_sums[2 * (kRsThreads / 32)];
+    __shared__ int s_flag, s_nvalid, s_nsafe, s_nsurv, s_lbest;
 
     const int p = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -424,47 +434,73 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
         return;
     }
 
-    // ---------------- pass 0: which hypotheses pass the orientation / collinearity test (ordered compaction)
+    // ---------------- pass 0: which hypotheses pass the orientation / collinearity test (ordered compaction);
+    // those with a provably safe denominator go first (vlist[0, n_safe)), the others after them
     {
-        int base = 0;
+        int base = 0, base_u = 0;
         for (int h0 = 0; h0 < a.n_hyp; h0 += kRsThreads) {
             const int hyp = h0 + tid;
-            int ok = 0;
+            int ok = 0, safe = 0;
             if (hyp < a.n_hyp) {
                 int idx[4];
                 sample4(a.seed, pair_level, static_cast<uint32_t>(hyp), m, idx);
                 const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
                 double H[9];
                 ok = solve4(q, H) ? 1 : 0;
+                safe = ok && den_safe(static_cast<float>(H[6]), static_cast<float>(H[7]), cmax);
             }
-            const unsigned bal = __ballot_sync(0xffffffff, ok);
-            if (lane == 0) warp_sums[warp] = __popc(bal);
+            const unsigned bal_s = __ballot_sync(0xffffffff, safe);
+            const unsigned bal_u = __ballot_sync(0xffffffff, ok && !safe);
+            if (lane == 0) { warp_sums[warp] = __popc(bal_s); warp_sums[kRsThreads / 32 + warp] = __popc(bal_u); }
             __syncthreads();
-            int before = 0, total = 0;
+            int before = 0, total = 0, before_u = 0, total_u = 0;
 #pragma unroll
-            for (int w = 0; w < kRsThreads / 32; ++w) { const int c = warp_sums[w]; before += w < warp ? c : 0; total += c; }
-            if (ok) vlist[base + before + __popc(bal & ((1u << lane) - 1u))] = static_cast<uint16_t>(hyp);
-            base += total;
+            for (int w = 0; w < kRsThreads / 32; ++w) {
+                const int c = warp_sums[w], cu = warp_sums[kRsThreads / 32 + w];
+                before += w < warp ? c : 0; total += c;
+                before_u += w < warp ? cu : 0; total_u += cu;
+            }
+            const unsigned below = (1u << lane) - 1u;
+            if (safe) vlist[base + before + __popc(bal_s & below)] = static_cast<uint16_t>(hyp);
+            else if (ok) slist[base_u + before_u + __popc(bal_u & below)] = static_cast<uint16_t>(hyp);
+            base += total; base_u += total_u;
             __syncthreads();
         }
-        if (tid == 0) s_nvalid = base;
+        for (int k = tid; k < base_u; k += kRsThreads) vlist[base + k] = slist[k];
+        if (tid == 0) { s_nvalid = base + base_u; s_nsafe = base; }
     }
     __syncthreads();
-    const int n_valid = s_nvalid;
+    const int n_valid = s_nvalid, n_safe = s_nsafe;
 
     // ---------------- pass 1: fused scoring of the valid hypotheses with count bounds [lo, hi]
     unsigned long long best_key = 0;      // (exact count << 32) | ~hyp   of hypotheses whose count is already exact
-    for (int s0 = 0; s0 < n_valid; s0 += kRsThreads * kHpt) {
-        // live hypotheses per thread in this batch (1..kHpt): idle slots are not evaluated
-        const int nj = min(kHpt, (n_valid - s0 + kRsThreads - 1) / kRsThreads);
-        int my_lo;
-        switch (nj) {
-            case 1:  my_lo = score_batch<1>(a, pts, vlist, lo_s, hi_s, s0, n_valid, m, cmax, pair_level); break;
-            case 2:  my_lo = score_batch<2>(a, pts, vlist, lo_s, hi_s, s0, n_valid, m, cmax, pair_level); break;
-            case 3:  my_lo = score_batch<3>(a, pts, vlist, lo_s, hi_s, s0, n_valid, m, cmax, pair_level); break;
-            default: my_lo = score_batch<4>(a, pts, vlist, lo_s, hi_s, s0, n_valid, m, cmax, pair_level); break;
+#pragma unroll 1
+    for (int region = 0; region < 2; ++region) {
+        // whole rows of kRsThreads safe slots run without the denominator test; the remaining safe slots share
+        // their rows with the unsafe ones (never more thread-rows than a single region would need)
+        const int n_nochk = n_safe / kRsThreads * kRsThreads;
+        const int r_begin = region ? n_nochk : 0, r_end = region ? n_valid : n_nochk;
+        for (int s0 = r_begin; s0 < r_end; s0 += kRsThreads * kHpt) {
+            // live hypotheses per thread in this batch (1..kHpt): idle slots are not evaluated
+            const int nj = min(kHpt, (r_end - s0 + kRsThreads - 1) / kRsThreads);
+            int my_lo;
+            if (region == 0) {
+                switch (nj) {
+                    case 1:  my_lo = score_batch<1, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
+                    case 2:  my_lo = score_batch<2, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
+                    case 3:  my_lo = score_batch<3, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
+                    default: my_lo = score_batch<4, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
+                }
+            } else {
+                switch (nj) {
+                    case 1:  my_lo = score_batch<1, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
+                    case 2:  my_lo = score_batch<2, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
+                    case 3:  my_lo = score_batch<3, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
+                    default: my_lo = score_batch<4, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
+                }
+            }
+            atomicMax(&s_lbest, my_lo);
         }
-        atomicMax(&s_lbest, my_lo);
     }
     __syncthreads();
     const int lbest = s_lbest;

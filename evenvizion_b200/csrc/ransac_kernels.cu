@@ -369,6 +369,61 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
     return my_lo;
 }
 
+// The last, partially filled row of hypotheses (L < kRsThreads live slots starting at r0): instead of
+// letting most threads idle through all m matches, the threads are regrouped as (hypothesis, slice): Lp =
+// L rounded up to a power of two >= 32, slice = tid / Lp of kRsThreads / Lp slices, and every slice scores
+// a strided share of the matches; partial counts meet in shared memory.  Same classification per
+// evaluation as score_batch<.., true>, so the bounds are identical.
+__device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4* pts, const uint16_t* vlist,
+                                                  uint16_t* lo_s, uint16_t* hi_s, int* part, int* lbest, int r0, int L, int m,
+                                                  float cmax, uint32_t pair_level) {
+    const int tid = threadIdx.x;
+    int Lp = 32;
+    while (Lp < L) Lp <<= 1;
+    const int slices = kRsThreads / Lp;
+    const int k = tid & (Lp - 1), slice = tid / Lp;
+    const bool live = k < L;
+    float hf[8];
+    float tlo = -INFINITY, thi = -INFINITY;                  // idle lane: everything "sure out"
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hf[i] = 0.f;
+    if (live) {
+        int idx[4];
+        sample4(a.seed, pair_level, static_cast<uint32_t>(vlist[r0 + k]), m, idx);
+        const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
+        double H[9];
+        solve4(q, H);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hf[i] = static_cast<float>(H[i]);
+        fused_thresholds(hf, cmax, a.thresh2, a.exact_only != 0, tlo, thi);
+    }
+    part[tid] = 0; part[kRsThreads + tid] = 0;
+    __syncthreads();
+    int lo = 0, out = 0;
+    for (int i = slice; i < m; i += slices) {
+        const float4 pt = pts[i];
+        const float den = __fmaf_rn(hf[6], pt.x, __fmaf_rn(hf[7], pt.y, 1.f));
+        float ww;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ww) : "f"(den));
+        const float X = __fmaf_rn(hf[0], pt.x, __fmaf_rn(hf[1], pt.y, hf[2]));
+        const float Y = __fmaf_rn(hf[3], pt.x, __fmaf_rn(hf[4], pt.y, hf[5]));
+        const float dx = __fmaf_rn(X, ww, -pt.z);
+        const float dy = __fmaf_rn(Y, ww, -pt.w);
+        const float e = __fmaf_rn(dx, dx, __fmul_rn(dy, dy));
+        const float e2 = fabsf(den) >= kDenMin ? e : __int_as_float(0x7fc00000);
+        asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(lo) : "f"(e2), "f"(tlo));
+        asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(out) : "f"(e2), "f"(thi));
+    }
+    if (live) { atomicAdd(&part[k], lo); atomicAdd(&part[kRsThreads + k], out); }
+    __syncthreads();
+    if (live && slice == 0) {
+        const int l = part[k];
+        lo_s[r0 + k] = static_cast<uint16_t>(l);
+        hi_s[r0 + k] = static_cast<uint16_t>(m - part[kRsThreads + k]);
+        atomicMax(lbest, l);
+    }
+}
+
 // dynamic shared memory of the scoring kernel: float4 pts[max_cnt] | u16 vlist, slist, lo_s, hi_s [n_hyp] each
 __global__ void __launch_bounds__(kRsThreads, 3)
 ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __restrict__ phase) {
@@ -381,6 +436,7 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     __shared__ unsigned long long red[kRsThreads / 32];
     __shared__ float cmax_s[kRsThreads / 32];
     __shared__ int warp_sums[2 * (kRsThreads / 32)];
+    __shared__ int part_s[2 * kRsThreads];
     __shared__ int s_flag, s_nvalid, s_nsafe, s_nsurv, s_lbest;
 
     const int p = blockIdx.x;
@@ -479,7 +535,8 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
         // whole rows of kRsThreads safe slots run without the denominator test; the remaining safe slots share
         // their rows with the unsafe ones (never more thread-rows than a single region would need)
         const int n_nochk = n_safe / kRsThreads * kRsThreads;
-        const int r_begin = region ? n_nochk : 0, r_end = region ? n_valid : n_nochk;
+        const int n_full = n_nochk + (n_valid - n_nochk) / kRsThreads * kRsThreads;     // end of the last full row
+        const int r_begin = region ? n_nochk : 0, r_end = region ? n_full : n_nochk;
         for (int s0 = r_begin; s0 < r_end; s0 += kRsThreads * kHpt) {
             // live hypotheses per thread in this batch (1..kHpt): idle slots are not evaluated
             const int nj = min(kHpt, (r_end - s0 + kRsThreads - 1) / kRsThreads);
@@ -501,6 +558,8 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
             }
             atomicMax(&s_lbest, my_lo);
         }
+        if (region == 1 && n_full < n_valid)
+            score_partial_row(a, pts, vlist, lo_s, hi_s, part_s, &s_lbest, n_full, n_valid - n_full, m, cmax, pair_level);
     }
     __syncthreads();
     const int lbest = s_lbest;

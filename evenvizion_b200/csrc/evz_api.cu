@@ -57,6 +57,7 @@ extern "C" int evz_set_option(evz_handle* h, int option, int value) {
     switch (option) {
         case EVZ_OPT_RANSAC_EXACT: h->opt_ransac_exact = value; return EVZ_OK;
         case EVZ_OPT_MATCH_VARIANT: h->opt_match_variant = value; return EVZ_OK;
+        case EVZ_OPT_RANSAC_NO_PRUNE: h->opt_ransac_no_prune = value; return EVZ_OK;
         default: EVZ_SET_ERR(h, "evz_set_option: unknown option %d", option); return EVZ_E_ARG;
     }
 }

@@ -27,6 +27,7 @@ struct evz_handle {
     bool match_attr_set = false;
     // options (evz_set_option)
     int opt_ransac_exact = 0;
+    int opt_ransac_no_prune = 0;
     int opt_match_variant = 0;
 };
 

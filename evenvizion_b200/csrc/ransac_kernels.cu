@@ -29,6 +29,7 @@ namespace evz {
 constexpr int kRsThreads = 256;   // scoring kernel
 constexpr int kRfThreads = 64;    // refit kernel
 constexpr int kHpt = 4;           // hypotheses scored concurrently per thread
+constexpr int kProbe = 64;        // hypotheses of the level-2 probe row (see ransac_score_kernel)
 constexpr int kLmMaxIters = 20;   // OpenCV uses 10 from a DLT start; we start from the 4-point model
 constexpr int kNSums = 32;        // 21 JtJ + 8 Jtr + S + max|r| (+1 pad)
 
@@ -130,6 +131,7 @@ struct FhArgs {
     int32_t* best_hyp; int32_t* best_cnt; uint8_t* mask_best; double* H_best;
     int max_cnt;
     int exact_only;
+    int no_prune;
 };
 
 // 8x8 symmetric positive-definite system through an LDL^T factorisation held in registers
@@ -318,7 +320,7 @@ __device__ __forceinline__ void fused_thresholds(const float (&h)[8], float cmax
 template <int NJ, bool kCheckDen>
 __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, const uint16_t* vlist,
                                            uint16_t* lo_s, uint16_t* hi_s, int s0, int n_valid, int m, float cmax,
-                                           uint32_t pair_level) {
+                                           uint32_t pair_level, int* cut) {
     const int tid = threadIdx.x;
     float hf[NJ][8];
     float tlo[NJ], thi[NJ];
@@ -363,7 +365,11 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int slot = s0 + j * kRsThreads + tid;
-        if (slot < n_valid) { lo_s[slot] = static_cast<uint16_t>(lo[j]); hi_s[slot] = static_cast<uint16_t>(m - out[j]); }
+        if (slot < n_valid) {
+            lo_s[slot] = static_cast<uint16_t>(lo[j]); hi_s[slot] = static_cast<uint16_t>(m - out[j]);
+            // every match is a sure inlier: no hypothesis with a larger index can win any more
+            if (lo[j] == m) atomicMin(cut, static_cast<int>(vlist[slot]));
+        }
         my_lo = max(my_lo, lo[j]);
     }
     return my_lo;
@@ -375,7 +381,7 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
 // a strided share of the matches; partial counts meet in shared memory.  Same classification per
 // evaluation as score_batch<.., true>, so the bounds are identical.
 __device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4* pts, const uint16_t* vlist,
-                                                  uint16_t* lo_s, uint16_t* hi_s, int* part, int* lbest, int r0, int L, int m,
+                                                  uint16_t* lo_s, uint16_t* hi_s, int* part, int* lbest, int* cut, int r0, int L, int m,
                                                   float cmax, uint32_t pair_level) {
     const int tid = threadIdx.x;
     int Lp = 32;
@@ -421,7 +427,9 @@ __device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4*
         lo_s[r0 + k] = static_cast<uint16_t>(l);
         hi_s[r0 + k] = static_cast<uint16_t>(m - part[kRsThreads + k]);
         atomicMax(lbest, l);
+        if (l == m) atomicMin(cut, static_cast<int>(vlist[r0 + k]));
     }
+    __syncthreads();                                         // part[] may be reused by a later call
 }
 
 // dynamic shared memory of the scoring kernel: float4 pts[max_cnt] | u16 vlist, slist, lo_s, hi_s [n_hyp] each
@@ -437,7 +445,7 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     __shared__ float cmax_s[kRsThreads / 32];
     __shared__ int warp_sums[2 * (kRsThreads / 32)];
     __shared__ int part_s[2 * kRsThreads];
-    __shared__ int s_flag, s_nvalid, s_nsafe, s_nsurv, s_lbest;
+    __shared__ int s_flag, s_nvalid, s_nsafe, s_nsurv, s_lbest, s_cut;
 
     const int p = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -462,7 +470,7 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffff, cmax, of));
     if (lane == 0) cmax_s[warp] = cmax;
-    if (tid == 0) { s_nvalid = 0; s_nsurv = 0; s_lbest = 0; }
+    if (tid == 0) { s_nvalid = 0; s_nsurv = 0; s_lbest = 0; s_cut = 0x7FFFFFFF; }
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < kRsThreads / 32; ++w) cmax = fmaxf(cmax, cmax_s[w]);
@@ -530,36 +538,69 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
 
     // ---------------- pass 1: fused scoring of the valid hypotheses with count bounds [lo, hi]
     unsigned long long best_key = 0;      // (exact count << 32) | ~hyp   of hypotheses whose count is already exact
+    const bool prune = a.exact_only == 0 && a.no_prune == 0;
+    for (int slot = tid; slot < n_valid; slot += kRsThreads) { lo_s[slot] = 0; hi_s[slot] = 0; }     // skipped slots: hi = 0
+    __syncthreads();
+    // Probe (level >= 2, where nearly every point is an inlier): the kProbe lowest-index hypotheses are scored
+    // first, sliced over the matches like a partial row.  If one of them counts every match as a sure
+    // inlier, everything after it is pruned below.
+    int start = 0;
+    if (prune && a.level >= 2 && n_valid > kProbe) {
+        score_partial_row(a, pts, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, 0, kProbe, m, cmax, pair_level);
+        start = kProbe;
+    }
+    // whole rows of kRsThreads safe slots run without the denominator test; the remaining safe slots share
+    // their rows with the unsafe ones (never more thread-rows than a single region would need)
+    const int n_nochk = start + max(0, n_safe - start) / kRsThreads * kRsThreads;
+    const int n_full = n_nochk + (n_valid - n_nochk) / kRsThreads * kRsThreads;     // end of the last full row
 #pragma unroll 1
     for (int region = 0; region < 2; ++region) {
-        // whole rows of kRsThreads safe slots run without the denominator test; the remaining safe slots share
-        // their rows with the unsafe ones (never more thread-rows than a single region would need)
-        const int n_nochk = n_safe / kRsThreads * kRsThreads;
-        const int n_full = n_nochk + (n_valid - n_nochk) / kRsThreads * kRsThreads;     // end of the last full row
-        const int r_begin = region ? n_nochk : 0, r_end = region ? n_full : n_nochk;
-        for (int s0 = r_begin; s0 < r_end; s0 += kRsThreads * kHpt) {
+        const int r_begin = region ? n_nochk : start, r_end = region ? n_full : n_nochk;
+        for (int s0 = r_begin; s0 < r_end; ) {
             // live hypotheses per thread in this batch (1..kHpt): idle slots are not evaluated
             const int nj = min(kHpt, (r_end - s0 + kRsThreads - 1) / kRsThreads);
+            // Exact pruning: once a hypothesis counts every match as a sure inlier (s_cut = its index), the
+            // arg-max (count desc, hypothesis asc) cannot be any hypothesis with a larger index.
+            if (prune) {
+                __syncthreads();                                   // s_cut of the previous batch is visible
+                const int cutv = s_cut;
+                int alive = 0;
+#pragma unroll
+                for (int j = 0; j < kHpt; ++j) {
+                    const int slot = s0 + j * kRsThreads + tid;
+                    if (j < nj && slot < r_end && static_cast<int>(vlist[slot]) < cutv) alive = 1;
+                }
+                if (!__syncthreads_or(alive)) { s0 += nj * kRsThreads; continue; }
+            }
             int my_lo;
             if (region == 0) {
                 switch (nj) {
-                    case 1:  my_lo = score_batch<1, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
-                    case 2:  my_lo = score_batch<2, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
-                    case 3:  my_lo = score_batch<3, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
-                    default: my_lo = score_batch<4, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
+                    case 1:  my_lo = score_batch<1, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
+                    case 2:  my_lo = score_batch<2, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
+                    case 3:  my_lo = score_batch<3, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
+                    default: my_lo = score_batch<4, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
                 }
             } else {
                 switch (nj) {
-                    case 1:  my_lo = score_batch<1, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
-                    case 2:  my_lo = score_batch<2, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
-                    case 3:  my_lo = score_batch<3, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
-                    default: my_lo = score_batch<4, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level); break;
+                    case 1:  my_lo = score_batch<1, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
+                    case 2:  my_lo = score_batch<2, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
+                    case 3:  my_lo = score_batch<3, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
+                    default: my_lo = score_batch<4, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
                 }
             }
             atomicMax(&s_lbest, my_lo);
+            s0 += nj * kRsThreads;
         }
-        if (region == 1 && n_full < n_valid)
-            score_partial_row(a, pts, vlist, lo_s, hi_s, part_s, &s_lbest, n_full, n_valid - n_full, m, cmax, pair_level);
+        if (region == 1 && n_full < n_valid) {
+            int alive = 1;
+            if (prune) {
+                __syncthreads();
+                const int slot = n_full + tid;
+                alive = __syncthreads_or(slot < n_valid && static_cast<int>(vlist[slot]) < s_cut);
+            }
+            if (alive)
+                score_partial_row(a, pts, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, n_full, n_valid - n_full, m, cmax, pair_level);
+        }
     }
     __syncthreads();
     const int lbest = s_lbest;
@@ -806,7 +847,7 @@ extern "C" int evz_find_homography(evz_handle* h, const float* pts, const int32_
     }
     const float t = static_cast<float>(thresh * thresh);
     evz::FhArgs a{pts, off, cnt, pre_H, n_hyp, seed, pair_id_base, level, t, min_inlier_frac, fail_status,
-                  status, H, mask, inl_cnt, best_hyp, best_cnt, mask_best, H_best, max_cnt, h->opt_ransac_exact};
+                  status, H, mask, inl_cnt, best_hyp, best_cnt, mask_best, H_best, max_cnt, h->opt_ransac_exact, h->opt_ransac_no_prune};
     evz::ransac_score_kernel<<<n_pairs, evz::kRsThreads, smem_score, st>>>(a, hb, phase);
     EVZ_LAUNCH_CHECK(h);
     evz::ransac_refit_kernel<<<n_pairs, evz::kRfThreads, smem_refit, st>>>(a, hb, phase);

@@ -82,6 +82,8 @@ int         evz_sm_count(const evz_handle* h);
 #define EVZ_OPT_MATCH_VARIANT  2  /* match epilogue: 0 default (chunk-8 minima + saved best chunk, 8 epilogue warps);
                                      1 exact top-2 per element (8 warps); 2 chunk 16 (8 warps); 3 chunk 8 (16 warps);
                                      4 exact top-2 per element (16 warps) */
+#define EVZ_OPT_RANSAC_NO_PRUNE 3  /* 1: score every valid hypothesis even after one of them counted all matches as inliers
+                                     (default 0: hypotheses that can no longer win the (count desc, index asc) arg-max are skipped) */
 int         evz_set_option(evz_handle* h, int option, int value);
 
 /* ---- ingest: the step before the path.  Replaces the implicit

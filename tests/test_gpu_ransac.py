@@ -162,3 +162,41 @@ def test_fused_fast_path_equals_exact_scoring(engine, scale, persp):
     i = 3
     ref = ransac.find_homography_seeded(sets[i][0], sets[i][1], 2048, 3, 50 + i, 1)
     assert int(f["best_hyp"][i]) == ref["hyp"]["best"] and int(f["best_cnt"][i]) == ref["hyp"]["best_count"]
+
+
+@pytest.mark.parametrize("level", [1, 2])
+def test_exact_pruning_equals_scoring_every_hypothesis(engine, level):
+    """Once a hypothesis counts every point as a sure inlier, hypotheses with a larger index cannot win the
+    (count desc, index asc) arg-max and are skipped (level 2 additionally probes the first 64).  The result
+    must equal scoring all hypotheses (EVZ_OPT_RANSAC_NO_PRUNE) and the oracle."""
+    rng = np.random.default_rng(77 + level)
+    sets = []
+    for k in range(40):
+        n = int(rng.integers(5, 900))
+        a = (rng.random((n, 2)) * [1920, 1080]).astype(np.float32)
+        th = rng.normal() * 0.01
+        Ht = np.array([[np.cos(th), -np.sin(th), rng.normal() * 5], [np.sin(th), np.cos(th), rng.normal() * 5],
+                       [rng.normal() * 1e-6, rng.normal() * 1e-6, 1]])
+        p = np.c_[a, np.ones(n)] @ Ht.T
+        noise = [0.0, 0.05, 0.3, 1.2][k % 4]              # k % 4 < 3: all-inlier sets (pruning fires); else mixed
+        b = (p[:, :2] / p[:, 2:] + rng.normal(size=(n, 2)) * noise).astype(np.float32)
+        if k % 8 == 7:
+            o = rng.random(n) < 0.3
+            b[o] = (rng.random((int(o.sum()), 2)) * [1920, 1080]).astype(np.float32)
+        sets.append((a, b))
+    pts, off, cnt, off_h, cnt_h = _pack(sets, engine.device)
+    outs = []
+    for no_prune in (0, 1):
+        engine.set_option(3, no_prune)
+        status = torch.zeros(len(sets), dtype=torch.int32, device=engine.device)
+        outs.append((engine.find_homography(pts, off, cnt, status, int(cnt_h.max()), 700, 9, 1000, level), status))
+    engine.set_option(3, 0)
+    (f, sf), (e, se) = outs
+    assert torch.equal(sf, se)
+    for k in ("best_hyp", "best_cnt", "mask_best", "H_best", "mask", "inl_cnt", "H"):
+        assert torch.equal(f[k], e[k]), k
+    fired = int((f["best_cnt"].cpu() == torch.from_numpy(cnt_h.astype(np.int32))).sum())
+    assert fired >= 10                                       # the pruned path was actually exercised
+    for i in (0, 1, 2, 7, 13):
+        ref = ransac.find_homography_seeded(sets[i][0], sets[i][1], 700, 9, 1000 + i, level)
+        assert int(f["best_hyp"][i]) == ref["hyp"]["best"] and int(f["best_cnt"][i]) == ref["hyp"]["best_count"]

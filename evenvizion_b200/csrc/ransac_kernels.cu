@@ -325,14 +325,17 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
     float hf[NJ][8];
     float tlo[NJ], thi[NJ];
     int lo[NJ], out[NJ];
+    bool live[NJ], any_live = false;
+    const int cutv = *cut;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int slot = s0 + j * kRsThreads + tid;
-        lo[j] = 0; out[j] = 0;
+        lo[j] = 0; out[j] = 0; live[j] = false;
         tlo[j] = -INFINITY; thi[j] = -INFINITY;            // idle slot: everything "sure out"
 #pragma unroll
         for (int i = 0; i < 8; ++i) hf[j][i] = 0.f;
-        if (slot < n_valid) {
+        // hypotheses behind the cut (see the pruning note in ransac_score_kernel) stay idle: lo = hi = 0
+        if (slot < n_valid && static_cast<int>(vlist[slot]) < cutv) {
             int idx[4];
             sample4(a.seed, pair_level, static_cast<uint32_t>(vlist[slot]), m, idx);
             const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
@@ -341,9 +344,12 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
 #pragma unroll
             for (int i = 0; i < 8; ++i) hf[j][i] = static_cast<float>(H[i]);
             fused_thresholds(hf[j], cmax, a.thresh2, a.exact_only != 0, tlo[j], thi[j]);
+            live[j] = true;
+            any_live = true;
         }
     }
-    for (int i = 0; i < m; ++i) {
+    const int m_eff = __any_sync(0xffffffff, any_live) ? m : 0;      // a warp without live hypotheses skips the matches
+    for (int i = 0; i < m_eff; ++i) {
         const float4 pt = pts[i];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
@@ -365,7 +371,7 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int slot = s0 + j * kRsThreads + tid;
-        if (slot < n_valid) {
+        if (live[j]) {
             lo_s[slot] = static_cast<uint16_t>(lo[j]); hi_s[slot] = static_cast<uint16_t>(m - out[j]);
             // every match is a sure inlier: no hypothesis with a larger index can win any more
             if (lo[j] == m) atomicMin(cut, static_cast<int>(vlist[slot]));
@@ -388,7 +394,7 @@ __device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4*
     while (Lp < L) Lp <<= 1;
     const int slices = kRsThreads / Lp;
     const int k = tid & (Lp - 1), slice = tid / Lp;
-    const bool live = k < L;
+    const bool live = k < L && static_cast<int>(vlist[r0 + k]) < *cut;     // behind the cut: idle, lo = hi = 0
     float hf[8];
     float tlo = -INFINITY, thi = -INFINITY;                  // idle lane: everything "sure out"
 #pragma unroll
@@ -406,7 +412,8 @@ __device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4*
     part[tid] = 0; part[kRsThreads + tid] = 0;
     __syncthreads();
     int lo = 0, out = 0;
-    for (int i = slice; i < m; i += slices) {
+    const int m_eff = __any_sync(0xffffffff, live) ? m : 0;          // a warp without live hypotheses skips the matches
+    for (int i = slice; i < m_eff; i += slices) {
         const float4 pt = pts[i];
         const float den = __fmaf_rn(hf[6], pt.x, __fmaf_rn(hf[7], pt.y, 1.f));
         float ww;
@@ -500,6 +507,8 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
 
     // ---------------- pass 0: which hypotheses pass the orientation / collinearity test (ordered compaction);
     // those with a provably safe denominator go first (vlist[0, n_safe)), the others after them
+    const bool prune = a.exact_only == 0 && a.no_prune == 0;
+    bool probed = false;
     {
         int base = 0, base_u = 0;
         for (int h0 = 0; h0 < a.n_hyp; h0 += kRsThreads) {
@@ -529,6 +538,15 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
             else if (ok) slist[base_u + before_u + __popc(bal_u & below)] = static_cast<uint16_t>(hyp);
             base += total; base_u += total_u;
             __syncthreads();
+            // Probe (level >= 2, where nearly every point is an inlier): as soon as the first chunk of
+            // hypotheses is classified, its kProbe lowest-index safe ones are scored, sliced over the matches
+            // like a partial row.  If one of them counts every match as a sure inlier, no hypothesis of a
+            // later chunk can win the (count desc, index asc) arg-max: they are not even sampled.
+            if (prune && a.level >= 2 && h0 == 0 && base >= kProbe) {
+                score_partial_row(a, pts, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, 0, kProbe, m, cmax, pair_level);
+                probed = true;
+                if (s_cut != 0x7FFFFFFF) break;
+            }
         }
         for (int k = tid; k < base_u; k += kRsThreads) vlist[base + k] = slist[k];
         if (tid == 0) { s_nvalid = base + base_u; s_nsafe = base; }
@@ -538,17 +556,9 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
 
     // ---------------- pass 1: fused scoring of the valid hypotheses with count bounds [lo, hi]
     unsigned long long best_key = 0;      // (exact count << 32) | ~hyp   of hypotheses whose count is already exact
-    const bool prune = a.exact_only == 0 && a.no_prune == 0;
-    for (int slot = tid; slot < n_valid; slot += kRsThreads) { lo_s[slot] = 0; hi_s[slot] = 0; }     // skipped slots: hi = 0
+    const int start = probed ? kProbe : 0;
+    for (int slot = start + tid; slot < n_valid; slot += kRsThreads) { lo_s[slot] = 0; hi_s[slot] = 0; }   // skipped slots: hi = 0
     __syncthreads();
-    // Probe (level >= 2, where nearly every point is an inlier): the kProbe lowest-index hypotheses are scored
-    // first, sliced over the matches like a partial row.  If one of them counts every match as a sure
-    // inlier, everything after it is pruned below.
-    int start = 0;
-    if (prune && a.level >= 2 && n_valid > kProbe) {
-        score_partial_row(a, pts, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, 0, kProbe, m, cmax, pair_level);
-        start = kProbe;
-    }
     // whole rows of kRsThreads safe slots run without the denominator test; the remaining safe slots share
     // their rows with the unsafe ones (never more thread-rows than a single region would need)
     const int n_nochk = start + max(0, n_safe - start) / kRsThreads * kRsThreads;
@@ -558,7 +568,8 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
         const int r_begin = region ? n_nochk : start, r_end = region ? n_full : n_nochk;
         for (int s0 = r_begin; s0 < r_end; ) {
             // live hypotheses per thread in this batch (1..kHpt): idle slots are not evaluated
-            const int nj = min(kHpt, (r_end - s0 + kRsThreads - 1) / kRsThreads);
+            // (at level >= 2 the first row goes alone: the rows after it are usually pruned by the cut it finds)
+            const int nj = (prune && a.level >= 2 && s0 == start) ? 1 : min(kHpt, (r_end - s0 + kRsThreads - 1) / kRsThreads);
             // Exact pruning: once a hypothesis counts every match as a sure inlier (s_cut = its index), the
             // arg-max (count desc, hypothesis asc) cannot be any hypothesis with a larger index.
             if (prune) {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- frame-pairs/s of the geometry hot path (match + RANSAC H + scan) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
 
 A step is one pass of the hot path over one batch of synthetic input:
   config 2 (default, BASELINE.json configs[1]): 2048 SIFT-like keypoints/frame x 10 000 frame
@@ -33,6 +33,11 @@ CONFIGS = {
             outlier_frac=0.2, unmatched_frac=0.0),
     4: dict(name="sharp motion: 20% inlier ratio, 4096 hypotheses/pair, none_H_processing=True", n_kp=2048, pairs=10000,
             n_hyp=4096, outlier_frac=0.8, unmatched_frac=0.02),
+    # strong scaling: the 100 000 pairs are split over the ranks; the step also remaps 8 object points per frame
+    # through the cumulative superposition.  The chain is a 10 000-frame synthetic chain repeated (the seam pairs
+    # have no correspondences and exercise the None-H forward fill).
+    5: dict(name="long video 100k frame pairs sharded over the GPUs + cumulative H scan + object-coord remap", n_kp=2048,
+            pairs=100000, n_hyp=1024, outlier_frac=0.2, unmatched_frac=0.0, strong=True, remap_points=8, tile=10),
 }
 KERNELS_PER_STEP = 2 + 1 + 2 + 1 + 2 + 7      # build_items+match, filter, score+refit, static, score+refit, scan (7 kernels)
 KERNELS_PER_STEP_MULTI = 2 + 1 + 2 + 1 + 2 + 7 + 7   # + the summary pass of the cross-GPU scan (fill x3, prod x3, summary)
@@ -182,21 +187,39 @@ def run_ours(args, cfg):
     P, N, n_hyp = cfg["pairs"], cfg["n_kp"], cfg["n_hyp"]
     if args.pairs:
         P = args.pairs
+    strong = bool(cfg.get("strong"))
+    if strong:
+        P = P // world                      # strong scaling: the job's pairs are split over the ranks
+    K = int(cfg.get("remap_points", 0))
 
     # synthetic shard of this rank: a contiguous range of a (world * P)-pair video
-    ch = synth.make_chain(P + 1, N, seed=rank, device=dev, outlier_frac=cfg["outlier_frac"],
-                          unmatched_frac=cfg["unmatched_frac"])
+    tile = int(cfg.get("tile", 1))
+    if tile > 1 and P + 1 >= 2 * tile:
+        base_f = -(-(P + 1) // tile)
+        ch = synth.make_chain(base_f, N, seed=rank, device=dev, outlier_frac=cfg["outlier_frac"],
+                              unmatched_frac=cfg["unmatched_frac"])
+        ch = dict(desc=ch["desc"].repeat(tile, 1, 1)[:P + 1].contiguous(), coords=ch["coords"].repeat(tile, 1, 1)[:P + 1].contiguous())
+    else:
+        ch = synth.make_chain(P + 1, N, seed=rank, device=dev, outlier_frac=cfg["outlier_frac"],
+                              unmatched_frac=cfg["unmatched_frac"])
     desc_h = torch.empty(ch["desc"].shape, dtype=torch.uint8).pin_memory()
     coords_h = torch.empty(ch["coords"].shape, dtype=torch.float32).pin_memory()
     desc_h.copy_(ch["desc"]); coords_h.copy_(ch["coords"])
     torch.cuda.synchronize()
     st = eng.ingest(ch["desc"], ch["coords"])
+    torch.cuda.synchronize()
+    st.keep = ()                            # the raw staging copies are consumed: free them (26 GB at config 5)
+    del ch
     pq = torch.arange(1, P + 1, dtype=torch.int32, device=dev)
     pt = torch.arange(0, P, dtype=torch.int32, device=dev)
     pair_base = rank * P
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     match_ms, ransac_ms = [], []
+    if K:
+        g = torch.Generator(device=dev); g.manual_seed(99 + rank)
+        obj_pts = torch.rand((P * K, 2), generator=g, device=dev, dtype=torch.float64) * torch.tensor([1920.0, 1080.0], device=dev, dtype=torch.float64)
+        obj_frame = torch.arange(P, dtype=torch.int32, device=dev).repeat_interleave(K).contiguous()
 
     def step(timed):
         e = [ev() for _ in range(4)] if timed else None
@@ -215,6 +238,8 @@ def run_ours(args, cfg):
                                       seed_G=None if sG is None else torch.from_numpy(sG.reshape(9)).to(dev))
         else:
             S, Hf, _ = eng.chain_scan(h2["H"], r.status, True)
+        if K:
+            fixed = eng.remap(obj_pts, obj_frame, S, 400.0 / 1920.0, 224.0 / 1080.0, False)     # frames 2.. of the shard
         if timed: e[3].record()
         return r, S, e
 
@@ -246,14 +271,19 @@ def run_ours(args, cfg):
         match_ms.append(e[0].elapsed_time(e[1])); ransac_ms.append(e[1].elapsed_time(e[2]))
     n_ok = int((r.status == 0).sum().item())
     mean_matches = float(r.m_cnt.float().mean().item())
+    del r
 
     # ---- end to end through the public host API (pinned host buffers in, host arrays out)
+    del S
+    out = None
     for _ in range(2):
+        out = None
         out = eng.video_geometry(desc_h, coords_h, n_hyp=n_hyp, seed=0, pair_id_base=pair_base)
     sync_all()
     w0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
     for _ in range(e2e_steps):
+        out = None
         out = eng.video_geometry(desc_h, coords_h, n_hyp=n_hyp, seed=0, pair_id_base=pair_base)
     sync_all()
     e2e_ms = (time.perf_counter() - w0) * 1e3 / e2e_steps
@@ -287,10 +317,10 @@ def run_ours(args, cfg):
         print(json.dumps({
             "metric": "frame-pairs/sec (match+RANSAC H)", "value": world * P / (ms_per_step * 1e-3), "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 (s32 accumulate) match; f32/f64 RANSAC",
-            "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "u8 (s32 accumulate) match; f32/f64 RANSAC", "data": "synthetic",
             "config": {"workload": cfg["name"], "n_kp": N, "pairs_per_gpu": P, "n_hyp": n_hyp, "parallelism": f"pair-range x{world}",
-                       "l2": "inputs 2.6 GB per step > 126 MB L2, no flush", "valid_pairs_last_step": n_ok,
+                       "l2": f"inputs {(P + 1) * N * 136 / 1e9:.1f} GB per step > 126 MB L2, no flush", "valid_pairs_last_step": n_ok,
                        "mean_matches_per_pair": mean_matches},
             "stage_ms": {"match": m_ms, "ransac_static_ransac": float(np.mean(ransac_ms)),
                          "scan": ms_per_step - m_ms - float(np.mean(ransac_ms))},
@@ -304,7 +334,7 @@ def run_ours(args, cfg):
             "cpu_baseline": cpu,
             "e2e": {"value": world * P / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
-            "gpu_launches": (KERNELS_PER_STEP_MULTI if world > 1 else KERNELS_PER_STEP) * args.steps,
+            "gpu_launches": ((KERNELS_PER_STEP_MULTI if world > 1 else KERNELS_PER_STEP) + (1 if K else 0)) * args.steps,
             "clocks": clocks, "peaks": pk,
         }))
     if world > 1:

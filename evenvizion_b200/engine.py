@@ -422,6 +422,7 @@ class GeometryEngine:
             # pairs whose query frame is in this chunk (their train frame landed with this or an earlier chunk)
             self._pairs_range(st, r, max(f0, 1) - 1, f1 - 1, n_hyp, seed, pair_id_base, ratio, thresh)
         desc_raw.record_stream(copy); coords_raw.record_stream(copy)
+        st.keep = (bad,)                     # every consumer of the raw staging copies is enqueued: let them go
         if is_f32 and int(bad.item()):
             raise ValueError(f"{int(bad.item())} descriptor values are not integers in [0,255]; "
                              "the int8 tensor-core matcher is exact only for SIFT/ORB-style descriptors")

@@ -185,6 +185,9 @@ class GeometryEngine:
 
     # ------------------------------------------------------------------ K1 / K1b / K2
     def match(self, st: FrameStore, pair_q, pair_t, ratio=0.5, min_matching_pts=4) -> PairResults:
+        """K1 + K1b/K2 for the pairs (pair_q[p], pair_t[p]).  Per-row outputs of pair p start at
+        out_off[p] = row_off[pair_q[p]], so one call must not list the same query frame twice (the C ABI
+        takes out_off as an argument and has no such restriction)."""
         pq = torch.as_tensor(pair_q, dtype=torch.int32).to(self.device)
         pt = torch.as_tensor(pair_t, dtype=torch.int32).to(self.device)
         P = int(pq.numel())

@@ -317,20 +317,26 @@ __device__ __forceinline__ void fused_thresholds(const float (&h)[8], float cmax
 // writes the count bounds of every live slot and returns the thread's best lower bound.
 // kCheckDen = false is used for hypotheses whose denominator provably stays >= kDenMin over the data range
 // (den_safe below), for which the per-evaluation |den| test can never fire.
+// Range of matches a scoring call covers.  FULL: all matches, final bounds.  PREFIX: matches [0, i1), the raw
+// partial counts (sure-in, sure-out) are parked in lo_s / hi_s.  SUFFIX: matches [i0, m) on top of the parked
+// partial counts, final bounds.  (Two-phase scoring, see ransac_score_kernel.)
+struct PtRange { int i0, i1, mode; };
+constexpr int kFull = 0, kPrefix = 1, kSuffix = 2;
+
 template <int NJ, bool kCheckDen>
 __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, const uint16_t* vlist,
                                            uint16_t* lo_s, uint16_t* hi_s, int s0, int n_valid, int m, float cmax,
-                                           uint32_t pair_level, int* cut) {
+                                           uint32_t pair_level, int* cut, const PtRange rg) {
     const int tid = threadIdx.x;
     float hf[NJ][8];
     float tlo[NJ], thi[NJ];
     int lo[NJ], out[NJ];
-    bool live[NJ], any_live = false;
+    bool any_live = false;                                 // (a live slot is recognisable by thi > -inf)
     const int cutv = *cut;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int slot = s0 + j * kRsThreads + tid;
-        lo[j] = 0; out[j] = 0; live[j] = false;
+        lo[j] = 0; out[j] = 0;
         tlo[j] = -INFINITY; thi[j] = -INFINITY;            // idle slot: everything "sure out"
 #pragma unroll
         for (int i = 0; i < 8; ++i) hf[j][i] = 0.f;
@@ -344,12 +350,12 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
 #pragma unroll
             for (int i = 0; i < 8; ++i) hf[j][i] = static_cast<float>(H[i]);
             fused_thresholds(hf[j], cmax, a.thresh2, a.exact_only != 0, tlo[j], thi[j]);
-            live[j] = true;
             any_live = true;
+            if (rg.mode == kSuffix) { lo[j] = lo_s[slot]; out[j] = hi_s[slot]; }
         }
     }
-    const int m_eff = __any_sync(0xffffffff, any_live) ? m : 0;      // a warp without live hypotheses skips the matches
-    for (int i = 0; i < m_eff; ++i) {
+    const int i_end = __any_sync(0xffffffff, any_live) ? rg.i1 : 0;   // a warp without live hypotheses skips the matches
+    for (int i = rg.i0; i < i_end; ++i) {
         const float4 pt = pts[i];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
@@ -371,12 +377,16 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int slot = s0 + j * kRsThreads + tid;
-        if (live[j]) {
-            lo_s[slot] = static_cast<uint16_t>(lo[j]); hi_s[slot] = static_cast<uint16_t>(m - out[j]);
-            // every match is a sure inlier: no hypothesis with a larger index can win any more
-            if (lo[j] == m) atomicMin(cut, static_cast<int>(vlist[slot]));
+        if (thi[j] > -INFINITY) {
+            if (rg.mode == kPrefix) {
+                lo_s[slot] = static_cast<uint16_t>(lo[j]); hi_s[slot] = static_cast<uint16_t>(out[j]);
+            } else {
+                lo_s[slot] = static_cast<uint16_t>(lo[j]); hi_s[slot] = static_cast<uint16_t>(m - out[j]);
+                // every match is a sure inlier: no hypothesis with a larger index can win any more
+                if (lo[j] == m) atomicMin(cut, static_cast<int>(vlist[slot]));
+                my_lo = max(my_lo, lo[j]);
+            }
         }
-        my_lo = max(my_lo, lo[j]);
     }
     return my_lo;
 }
@@ -388,7 +398,7 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
 // evaluation as score_batch<.., true>, so the bounds are identical.
 __device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4* pts, const uint16_t* vlist,
                                                   uint16_t* lo_s, uint16_t* hi_s, int* part, int* lbest, int* cut, int r0, int L, int m,
-                                                  float cmax, uint32_t pair_level) {
+                                                  float cmax, uint32_t pair_level, const PtRange rg) {
     const int tid = threadIdx.x;
     int Lp = 32;
     while (Lp < L) Lp <<= 1;
@@ -412,8 +422,8 @@ __device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4*
     part[tid] = 0; part[kRsThreads + tid] = 0;
     __syncthreads();
     int lo = 0, out = 0;
-    const int m_eff = __any_sync(0xffffffff, live) ? m : 0;          // a warp without live hypotheses skips the matches
-    for (int i = slice; i < m_eff; i += slices) {
+    const int i_end = __any_sync(0xffffffff, live) ? rg.i1 : 0;      // a warp without live hypotheses skips the matches
+    for (int i = rg.i0 + slice; i < i_end; i += slices) {
         const float4 pt = pts[i];
         const float den = __fmaf_rn(hf[6], pt.x, __fmaf_rn(hf[7], pt.y, 1.f));
         float ww;
@@ -430,13 +440,80 @@ __device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4*
     if (live) { atomicAdd(&part[k], lo); atomicAdd(&part[kRsThreads + k], out); }
     __syncthreads();
     if (live && slice == 0) {
-        const int l = part[k];
+        int l = part[k], o = part[kRsThreads + k];
+        if (rg.mode == kSuffix) { l += lo_s[r0 + k]; o += hi_s[r0 + k]; }
         lo_s[r0 + k] = static_cast<uint16_t>(l);
-        hi_s[r0 + k] = static_cast<uint16_t>(m - part[kRsThreads + k]);
-        atomicMax(lbest, l);
-        if (l == m) atomicMin(cut, static_cast<int>(vlist[r0 + k]));
+        if (rg.mode == kPrefix) {
+            hi_s[r0 + k] = static_cast<uint16_t>(o);
+        } else {
+            hi_s[r0 + k] = static_cast<uint16_t>(m - o);
+            atomicMax(lbest, l);
+            if (l == m) atomicMin(cut, static_cast<int>(vlist[r0 + k]));
+        }
     }
     __syncthreads();                                         // part[] may be reused by a later call
+}
+
+// Scores the slots [s_begin, s_end) of vlist over the match range rg: whole rows of kRsThreads slots in
+// batches of up to kHpt rows (rows that lie entirely below n_safe run without the denominator test; the
+// remaining safe slots share their rows with the unsafe ones, never more thread-rows than a single region
+// would need), then the last partial row sliced over the matches.  With `prune`, batches and rows whose
+// hypotheses all lie behind the cut are skipped.
+__device__ __forceinline__ void score_slots(const FhArgs& a, const float4* pts, const uint16_t* vlist, uint16_t* lo_s,
+                                            uint16_t* hi_s, int* part_s, int* s_lbest, int* s_cut, int s_begin, int s_end,
+                                            int n_safe, int m, float cmax, uint32_t pair_level, bool prune,
+                                            bool first_row_alone, const PtRange rg) {
+    const int tid = threadIdx.x;
+    if (s_end <= s_begin) return;
+    const int n_nochk = s_begin + max(0, min(n_safe, s_end) - s_begin) / kRsThreads * kRsThreads;
+    const int n_full = n_nochk + (s_end - n_nochk) / kRsThreads * kRsThreads;     // end of the last full row
+#pragma unroll 1
+    for (int region = 0; region < 2; ++region) {
+        const int r_begin = region ? n_nochk : s_begin, r_end = region ? n_full : n_nochk;
+        for (int s0 = r_begin; s0 < r_end; ) {
+            // live hypotheses per thread in this batch (1..kHpt): idle slots are not evaluated
+            const int nj = (first_row_alone && s0 == s_begin) ? 1 : min(kHpt, (r_end - s0 + kRsThreads - 1) / kRsThreads);
+            if (prune) {
+                __syncthreads();                                   // s_cut of the previous batch is visible
+                const int cutv = *s_cut;
+                int alive = 0;
+#pragma unroll
+                for (int j = 0; j < kHpt; ++j) {
+                    const int slot = s0 + j * kRsThreads + tid;
+                    if (j < nj && slot < r_end && static_cast<int>(vlist[slot]) < cutv) alive = 1;
+                }
+                if (!__syncthreads_or(alive)) { s0 += nj * kRsThreads; continue; }
+            }
+            int my_lo;
+            if (region == 0) {
+                switch (nj) {
+                    case 1:  my_lo = score_batch<1, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    case 2:  my_lo = score_batch<2, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    case 3:  my_lo = score_batch<3, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    default: my_lo = score_batch<4, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                }
+            } else {
+                switch (nj) {
+                    case 1:  my_lo = score_batch<1, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    case 2:  my_lo = score_batch<2, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    case 3:  my_lo = score_batch<3, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    default: my_lo = score_batch<4, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                }
+            }
+            atomicMax(s_lbest, my_lo);
+            s0 += nj * kRsThreads;
+        }
+        if (region == 1 && n_full < s_end) {
+            int alive = 1;
+            if (prune) {
+                __syncthreads();
+                const int slot = n_full + tid;
+                alive = __syncthreads_or(slot < s_end && static_cast<int>(vlist[slot]) < *s_cut);
+            }
+            if (alive)
+                score_partial_row(a, pts, vlist, lo_s, hi_s, part_s, s_lbest, s_cut, n_full, s_end - n_full, m, cmax, pair_level, rg);
+        }
+    }
 }
 
 // dynamic shared memory of the scoring kernel: float4 pts[max_cnt] | u16 vlist, slist, lo_s, hi_s [n_hyp] each
@@ -543,7 +620,7 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
             // like a partial row.  If one of them counts every match as a sure inlier, no hypothesis of a
             // later chunk can win the (count desc, index asc) arg-max: they are not even sampled.
             if (prune && a.level >= 2 && h0 == 0 && base >= kProbe) {
-                score_partial_row(a, pts, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, 0, kProbe, m, cmax, pair_level);
+                score_partial_row(a, pts, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, 0, kProbe, m, cmax, pair_level, PtRange{0, m, kFull});
                 probed = true;
                 if (s_cut != 0x7FFFFFFF) break;
             }
@@ -552,66 +629,71 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
         if (tid == 0) { s_nvalid = base + base_u; s_nsafe = base; }
     }
     __syncthreads();
-    const int n_valid = s_nvalid, n_safe = s_nsafe;
+    int n_valid = s_nvalid, n_safe = s_nsafe;
 
     // ---------------- pass 1: fused scoring of the valid hypotheses with count bounds [lo, hi]
     unsigned long long best_key = 0;      // (exact count << 32) | ~hyp   of hypotheses whose count is already exact
     const int start = probed ? kProbe : 0;
     for (int slot = start + tid; slot < n_valid; slot += kRsThreads) { lo_s[slot] = 0; hi_s[slot] = 0; }   // skipped slots: hi = 0
     __syncthreads();
-    // whole rows of kRsThreads safe slots run without the denominator test; the remaining safe slots share
-    // their rows with the unsafe ones (never more thread-rows than a single region would need)
-    const int n_nochk = start + max(0, n_safe - start) / kRsThreads * kRsThreads;
-    const int n_full = n_nochk + (n_valid - n_nochk) / kRsThreads * kRsThreads;     // end of the last full row
-#pragma unroll 1
-    for (int region = 0; region < 2; ++region) {
-        const int r_begin = region ? n_nochk : start, r_end = region ? n_full : n_nochk;
-        for (int s0 = r_begin; s0 < r_end; ) {
-            // live hypotheses per thread in this batch (1..kHpt): idle slots are not evaluated
-            // (at level >= 2 the first row goes alone: the rows after it are usually pruned by the cut it finds)
-            const int nj = (prune && a.level >= 2 && s0 == start) ? 1 : min(kHpt, (r_end - s0 + kRsThreads - 1) / kRsThreads);
-            // Exact pruning: once a hypothesis counts every match as a sure inlier (s_cut = its index), the
-            // arg-max (count desc, hypothesis asc) cannot be any hypothesis with a larger index.
-            if (prune) {
-                __syncthreads();                                   // s_cut of the previous batch is visible
-                const int cutv = s_cut;
-                int alive = 0;
+    // Two-phase scoring at level 1 (exact): the first row is scored against every match, which gives a true
+    // lower bound lb on the winning count.  A hypothesis that collects more than m - lb sure outliers can no
+    // longer reach lb, so the other rows first see only the K0 = m - lb + margin leading matches (PREFIX);
+    // the hypotheses still in the race are compacted (order kept) and finish on the remaining matches
+    // (SUFFIX).  With 80 % inliers this retires every outlier-contaminated hypothesis after ~25 % of its work.
+    // (At level >= 2 the first row goes alone instead: the rows after it are usually pruned by the cut it finds.)
+    // One call site of score_slots in a small state machine keeps the kernel's code size down.
+    const int s1 = start + kRsThreads;
+    const bool two_phase = prune && a.level == 1 && n_valid > s1;
+    int lb = 0;
+    int sb = start, se = two_phase ? s1 : n_valid;
+    PtRange rg{0, m, kFull};
+    for (int state = 0; state < 3; ) {
+        score_slots(a, pts, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, sb, se, n_safe, m, cmax, pair_level, prune,
+                    state == 0 && prune && a.level >= 2, rg);
+        if (!two_phase || rg.mode == kSuffix || (state == 1 && rg.mode == kFull)) break;
+        __syncthreads();
+        if (state == 0) {
+            lb = s_lbest;
+            const int K0 = (m - lb + 48 + 31) & ~31;
+            sb = s1; se = n_valid;
+            if (lb >= 4 && K0 * 5 <= m * 3) rg = PtRange{0, K0, kPrefix};
+            state = 1;
+            continue;
+        }
+        // state 1, after the PREFIX pass: ordered in-place compaction of the hypotheses that can still reach lb
+        // (new position <= old position; every chunk is read, then written)
+        const int cutv = s_cut;
+        int base = s1, safe_alive = 0;
+        for (int c0 = s1; c0 < n_valid; c0 += kRsThreads) {
+            const int slot = c0 + tid;
+            int hyp = 0, l = 0, o = 0, alive = 0;
+            if (slot < n_valid) {
+                hyp = vlist[slot]; l = lo_s[slot]; o = hi_s[slot];
+                alive = (o <= m - lb && hyp < cutv) ? 1 : 0;
+            }
+            const unsigned bal = __ballot_sync(0xffffffff, alive);
+            const unsigned bal_sf = __ballot_sync(0xffffffff, alive && slot < n_safe);
+            if (lane == 0) { warp_sums[warp] = __popc(bal); warp_sums[kRsThreads / 32 + warp] = __popc(bal_sf); }
+            __syncthreads();
+            int before = 0, total = 0;
 #pragma unroll
-                for (int j = 0; j < kHpt; ++j) {
-                    const int slot = s0 + j * kRsThreads + tid;
-                    if (j < nj && slot < r_end && static_cast<int>(vlist[slot]) < cutv) alive = 1;
-                }
-                if (!__syncthreads_or(alive)) { s0 += nj * kRsThreads; continue; }
+            for (int w = 0; w < kRsThreads / 32; ++w) {
+                const int c = warp_sums[w];
+                before += w < warp ? c : 0; total += c; safe_alive += warp_sums[kRsThreads / 32 + w];
             }
-            int my_lo;
-            if (region == 0) {
-                switch (nj) {
-                    case 1:  my_lo = score_batch<1, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
-                    case 2:  my_lo = score_batch<2, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
-                    case 3:  my_lo = score_batch<3, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
-                    default: my_lo = score_batch<4, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
-                }
-            } else {
-                switch (nj) {
-                    case 1:  my_lo = score_batch<1, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
-                    case 2:  my_lo = score_batch<2, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
-                    case 3:  my_lo = score_batch<3, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
-                    default: my_lo = score_batch<4, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, &s_cut); break;
-                }
+            if (alive) {
+                const int d = base + before + __popc(bal & ((1u << lane) - 1u));
+                vlist[d] = static_cast<uint16_t>(hyp); lo_s[d] = static_cast<uint16_t>(l); hi_s[d] = static_cast<uint16_t>(o);
             }
-            atomicMax(&s_lbest, my_lo);
-            s0 += nj * kRsThreads;
+            base += total;
+            __syncthreads();
         }
-        if (region == 1 && n_full < n_valid) {
-            int alive = 1;
-            if (prune) {
-                __syncthreads();
-                const int slot = n_full + tid;
-                alive = __syncthreads_or(slot < n_valid && static_cast<int>(vlist[slot]) < s_cut);
-            }
-            if (alive)
-                score_partial_row(a, pts, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, n_full, n_valid - n_full, m, cmax, pair_level);
-        }
+        n_safe = min(n_safe, s1) + safe_alive;
+        n_valid = base;
+        se = n_valid;
+        rg = PtRange{rg.i1, m, kSuffix};
+        state = 2;
     }
     __syncthreads();
     const int lbest = s_lbest;

@@ -23,48 +23,70 @@ __device__ __forceinline__ int disp_bin(const double* H, const float4 p) {
     return static_cast<int>(rint(dist));                                      // half-to-even, like Python round()
 }
 
+constexpr int kSfWindow = 2048;            // displacement bins histogrammed at a time (the used range is usually < 100 wide)
+
+// One CTA per pair.  Pass A computes every point's rounded displacement once (f64) into shared memory and
+// the used range [rmin, rmax]; the histogram / first-occurrence tables only cover windows of that range
+// (typically a single window), instead of zeroing and scanning all EVZ_R_MAX + 2 bins; the compaction
+// compares the cached bins.  Shared memory: u16 r[EVZ_MAX_KP] | u32 hist[kSfWindow] | i32 first[kSfWindow].
 __global__ void __launch_bounds__(256)
 static_filter_kernel(const float* __restrict__ pts, const int32_t* __restrict__ off, const int32_t* __restrict__ cnt,
                      const double* __restrict__ Hs, const int32_t* __restrict__ status,
                      float* __restrict__ out_pts, int32_t* __restrict__ out_cnt, int32_t* __restrict__ best_r,
                      int32_t* __restrict__ flags, int32_t* __restrict__ r_out) {
     extern __shared__ __align__(16) uint8_t sf_smem[];
-    uint32_t* hist = reinterpret_cast<uint32_t*>(sf_smem);
-    int32_t* first = reinterpret_cast<int32_t*>(sf_smem + ((kBins + 1) / 2) * 4);
+    uint16_t* r_s = reinterpret_cast<uint16_t*>(sf_smem);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(sf_smem + EVZ_MAX_KP * 2);
+    int32_t* first = reinterpret_cast<int32_t*>(hist + kSfWindow);
     __shared__ unsigned long long red[8];
     __shared__ int warp_sums[32];
-    __shared__ int s_best, s_over;
+    __shared__ int s_best, s_rmin, s_rmax;
     const int p = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (status[p] != EVZ_ST_OK) { if (tid == 0) { out_cnt[p] = 0; best_r[p] = -1; flags[p] = 0; } return; }
-    const int m = cnt[p];
+    const int m = min(cnt[p], EVZ_MAX_KP);       // the frame store never holds more per frame (memory safety only)
     const int64_t o = off[p];
     double H[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) H[i] = Hs[static_cast<size_t>(p) * 9 + i];
-    for (int i = tid; i < (kBins + 1) / 2; i += blockDim.x) hist[i] = 0;
-    for (int i = tid; i < kBins; i += blockDim.x) first[i] = INT_MAX;
-    if (tid == 0) s_over = 0;
+    if (tid == 0) { s_rmin = INT_MAX; s_rmax = -1; }
     __syncthreads();
     const float4* P = reinterpret_cast<const float4*>(pts) + o;
+    int rmin = INT_MAX, rmax = -1;
     for (int i = tid; i < m; i += blockDim.x) {
         const int r = disp_bin(H, P[i]);
         if (r_out) r_out[o + i] = r;
-        atomicAdd(&hist[r >> 1], 1u << (16 * (r & 1)));
-        atomicMin(&first[r], i);
-        if (r > EVZ_R_MAX) s_over = 1;
+        r_s[i] = static_cast<uint16_t>(r);
+        rmin = min(rmin, r); rmax = max(rmax, r);
     }
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) {
+        rmin = min(rmin, __shfl_xor_sync(0xffffffff, rmin, of));
+        rmax = max(rmax, __shfl_xor_sync(0xffffffff, rmax, of));
+    }
+    if (lane == 0 && rmax >= 0) { atomicMin(&s_rmin, rmin); atomicMax(&s_rmax, rmax); }
     __syncthreads();
+    rmin = s_rmin; rmax = s_rmax;
     // arg-max over bins: (count desc, first-inserted asc)  == reference's strict '>' over dict order
     unsigned long long key = 0;
-    for (int b = tid; b < kBins; b += blockDim.x) {
-        const unsigned int c = (hist[b >> 1] >> (16 * (b & 1))) & 0xFFFFu;
-        if (c) {
-            const unsigned long long k = (static_cast<unsigned long long>(c) << 48) |
-                                         (static_cast<unsigned long long>(0xFFFFFFu - static_cast<unsigned int>(first[b])) << 24) |
-                                         static_cast<unsigned long long>(b);
-            key = k > key ? k : key;
+    for (int w0 = rmin; w0 <= rmax; w0 += kSfWindow) {
+        for (int i = tid; i < kSfWindow; i += blockDim.x) { hist[i] = 0; first[i] = INT_MAX; }
+        __syncthreads();
+        for (int i = tid; i < m; i += blockDim.x) {
+            const int b = static_cast<int>(r_s[i]) - w0;
+            if (b >= 0 && b < kSfWindow) { atomicAdd(&hist[b], 1u); atomicMin(&first[b], i); }
         }
+        __syncthreads();
+        for (int b = tid; b < kSfWindow; b += blockDim.x) {
+            const unsigned int c = hist[b];
+            if (c) {
+                const unsigned long long k = (static_cast<unsigned long long>(c) << 48) |
+                                             (static_cast<unsigned long long>(0xFFFFFFu - static_cast<unsigned int>(first[b])) << 24) |
+                                             static_cast<unsigned long long>(b + w0);
+                key = k > key ? k : key;
+            }
+        }
+        __syncthreads();
     }
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) { const unsigned long long u = __shfl_xor_sync(0xffffffff, key, of); key = u > key ? u : key; }
@@ -82,7 +104,7 @@ static_filter_kernel(const float* __restrict__ pts, const int32_t* __restrict__ 
         const int i = ib + tid;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         int keep = 0;
-        if (i < m) { v = P[i]; keep = disp_bin(H, v) == best; }
+        if (i < m) { v = P[i]; keep = static_cast<int>(r_s[i]) == best; }
         // block exclusive scan of keep
         int incl = keep;
 #pragma unroll
@@ -101,7 +123,7 @@ static_filter_kernel(const float* __restrict__ pts, const int32_t* __restrict__ 
         base += warp_sums[7];
         __syncthreads();
     }
-    if (tid == 0) { out_cnt[p] = base; best_r[p] = best; flags[p] = s_over ? EVZ_FLAG_DISP_OVERFLOW : 0; }
+    if (tid == 0) { out_cnt[p] = base; best_r[p] = best; flags[p] = rmax > EVZ_R_MAX ? EVZ_FLAG_DISP_OVERFLOW : 0; }
 }
 
 // ------------------------------------------------------------------------------------ K6
@@ -333,7 +355,7 @@ extern "C" int evz_static_filter(evz_handle* h, const float* pts, const int32_t*
     if (!h) return EVZ_E_ARG;
     EVZ_REQUIRE(h, pts && off && cnt && H && status && out_pts && out_cnt && best_r && flags, "null pointer");
     if (n_pairs <= 0) return EVZ_OK;
-    const int smem = ((evz::kBins + 1) / 2) * 4 + evz::kBins * 4;
+    const int smem = EVZ_MAX_KP * 2 + evz::kSfWindow * 8;
     static bool attr = false;
     if (!attr) {
         EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::static_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

@@ -6,7 +6,7 @@ import evenvizion_b200 as evz
 from evenvizion_b200 import synth
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
-variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 1]
+variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 5]
 eng = evz.GeometryEngine(0)
 ch = synth.make_chain(P + 1, N, seed=0, device="cuda")
 st = eng.ingest(ch["desc"], ch["coords"])

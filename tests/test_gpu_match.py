@@ -160,13 +160,13 @@ def test_match_epilogue_variants_agree(engine):
     d[3, 8:16] = d[3, 0:8]
     d[4, :] = d[4, 0:1]                   # a whole frame of identical descriptors
     st = engine.ingest(d, ch["coords"])
-    outs = []
-    for v in (0, 1, 2, 3, 4):
+    outs = {}
+    for v in (0, 1, 2, 5):
         engine.set_option(2, v)
-        outs.append(engine.match(st, list(range(1, 6)), list(range(0, 5))))
+        outs[v] = engine.match(st, list(range(1, 6)), list(range(0, 5)))
     engine.set_option(2, 0)
     q0 = int(st.row_off_h[1])
-    for v in (1, 2, 3, 4):
+    for v in (1, 2, 5):
         assert torch.equal(outs[0].top2_idx[q0:], outs[v].top2_idx[q0:]), v
         assert torch.equal(outs[0].top2_d2[q0:], outs[v].top2_d2[q0:]), v
     # and both equal the oracle on the tie-heavy pairs
@@ -180,7 +180,7 @@ def test_match_epilogue_variants_agree(engine):
 
 def _check_launch_against_gemm(engine, st, pq, pt, counts, dd, offs):
     outs = {}
-    for v in (0, 1, 2, 3, 4):
+    for v in (0, 1, 2, 5):
         engine.set_option(2, v)
         outs[v] = [engine.match(st, pq, pt) for _ in range(2 if v == 0 else 1)]
     engine.set_option(2, 0)
@@ -233,3 +233,17 @@ def test_match_ragged_stress_against_device_reference(engine):
     # pairs first, then self-matches and non-adjacent pairs
     _check_launch_against_gemm(engine, st, list(range(1, F)), list(range(0, F - 1)), counts, dd, offs)
     _check_launch_against_gemm(engine, st, [5, 0, 17, 33, 60], [5, 40, 17, 2, 88], counts, dd, offs)
+
+
+def test_match_wide_norm_range_falls_back(engine):
+    """A train frame whose norm range exceeds what the fifth K block of the V-space kernel can encode
+    (hmax - hmin >= 1 951 004) goes through the legacy kernel, in the same launch as ordinary pairs."""
+    frames = _ragged_frames([300, 280, 310, 290, 520], seed=11)
+    frames[1][1][3] = 0
+    frames[1][1][7] = 255            # ||t||^2 from 0 to 8 323 200 inside frame 1
+    frames[3][1][5] = 255            # wide as a query frame only... and as the train frame of pair 3
+    st = _ingest(engine, frames)
+    pq, pt = [1, 2, 3, 4], [0, 1, 2, 3]
+    r = engine.match(st, pq, pt)
+    for p, (q, t) in enumerate(zip(pq, pt)):
+        _check_pair(engine, st, r, p, frames, q, t)

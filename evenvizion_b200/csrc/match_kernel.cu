@@ -631,24 +631,28 @@ __device__ __forceinline__ void vchunk(const uint32_t* r, uint32_t tagc, uint32_
     M2 = max(M2, t);
 }
 
-// one accumulator row (256 columns): 8 batches of 32 columns, TMEM loads one batch ahead; the accumulator is
+// one accumulator row (256 columns): 4 batches of 64 columns, TMEM loads one batch ahead (a batch takes
+// longer to process than a TMEM load takes to arrive; with batches of 32 it does not); the accumulator is
 // handed back to the MMA warp as soon as its last column is in registers
 __device__ __forceinline__ void drain_v(uint32_t taddr, uint32_t mul, uint32_t& M1, uint32_t& M2, uint32_t& M3,
                                         uint32_t& sec, uint32_t sum, uint64_t* acc_empty, int lane) {
-    uint32_t r[2][32];
-    tmem_ld_32x32b_x32(taddr, r[0]);
+    uint32_t r[2][2][32];
+    tmem_ld_32x32b_x32(taddr, r[0][0]);
+    tmem_ld_32x32b_x32(taddr + 32, r[0][1]);
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        tmem_ld_wait_dep(r[b & 1]);
-        if (b + 1 < 8) {
-            tmem_ld_32x32b_x32(taddr + (b + 1) * 32, r[(b + 1) & 1]);
+    for (int b = 0; b < 4; ++b) {
+        tmem_ld_wait_dep(r[b & 1][0]);
+        tmem_ld_wait_dep(r[b & 1][1]);
+        if (b + 1 < 4) {
+            tmem_ld_32x32b_x32(taddr + (b + 1) * 64, r[(b + 1) & 1][0]);
+            tmem_ld_32x32b_x32(taddr + (b + 1) * 64 + 32, r[(b + 1) & 1][1]);
         } else {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);
         }
-        vchunk(&r[b & 1][0], 254 - 2 * b, mul, M1, M2, M3, sec, sum);
-        vchunk(&r[b & 1][16], 253 - 2 * b, mul, M1, M2, M3, sec, sum);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vchunk(&r[b & 1][c >> 1][16 * (c & 1)], 254 - 4 * b - c, mul, M1, M2, M3, sec, sum);
     }
 }
 
@@ -702,21 +706,21 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
     const int n_items = *args.n_items;
 
     if (warp == 0) {
-        // ------------------------------------------------------------- TMA producer
+        // ------------------------------------------------------------- TMA producer (polling waits, single thread)
         if (lane == 0) {
             uint32_t stage = 0, sphase = 0, qi = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const Item im = load_item(args, it);
                 const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
                 ++qi;
-                mbar_wait(&q_empty[qb], qph ^ 1);
+                mbar_wait_spin(&q_empty[qb], qph ^ 1);
                 item_s[qb] = im;
                 if (im.n_tiles == 0) { mbar_arrive(&q_full[qb]); continue; }
                 mbar_arrive_expect_tx(&q_full[qb], kQBytes);
                 tma_load_2d(q_s + qb * kQBytes, &tmap, 0, im.q_row0, &q_full[qb]);
                 const uint8_t* ecode = args.ecode + static_cast<size_t>(im.t_row0 >> 8) * kECodeBytes;
                 for (int n = 0; n < im.n_tiles; ++n) {
-                    mbar_wait(&empty[stage], sphase ^ 1);
+                    mbar_wait_spin(&empty[stage], sphase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], kTileBytes + kECodeBytes);
                     tma_load_2d(t_s + stage * kTileBytes, &tmap, 0, im.t_row0 + n * kBlockT, &full[stage]);
                     bulk_load_1d(e_s + stage * kECodeBytes, ecode + static_cast<size_t>(n) * kECodeBytes, kECodeBytes, &full[stage]);

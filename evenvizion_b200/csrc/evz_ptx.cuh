@@ -49,14 +49,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 // spinning wait (test_wait never suspends the thread): for waits on the critical path of a kernel that has
 // issue slots to spare -- waking up from a suspended try_wait costs far more than the poll loop
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\t"
-                     "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    while (!mbar_test(bar, parity)) { __nanosleep(20); }      // short back-off: leave the issue slots to the warps that compute
 }
 
 // ---------------------------------------------------------------- TMA

@@ -99,6 +99,7 @@ struct MatchArgs {
     // V-space kernel only (match_top2_vkernel)
     const int32_t* pair_hmax;  // [n_pairs] max over the train frame of ||t||^2 >> 1
     const uint8_t* ecode;      // [total_rows / 256][8 KB] fifth K block of the train operand
+    const uint32_t* pbits;     // [total_rows / 256][8] parity of ||t||^2, one bit per train row
     uint32_t mul256;           // 256, passed at run time (keeps the chunk-key IMAD on the FMA pipe)
     int32_t* fix_count;        // number of rows left to match_fixup_kernel (reset by match_prepare_kernel)
     int32_t* fix_list;         // [fix_capacity] item * 256 + row
@@ -580,7 +581,9 @@ struct VCfg {
     static constexpr int slot_off  = a_off + 128 * 32;                 // [slot 2][part 4][row 256] x 16 B
     static constexpr int part_stride = 256 * 16;
     static constexpr int slot_stride = 4 * part_stride;
-    static constexpr int item_off  = slot_off + 2 * slot_stride;
+    static constexpr int pb_bytes  = (EVZ_MAX_KP / kBlockT) * 32;      // norm parity bitmap of one train frame
+    static constexpr int pb_off    = slot_off + 2 * slot_stride;       // 2 x pb_bytes, alternating per item
+    static constexpr int item_off  = pb_off + 2 * pb_bytes;
     static constexpr int bar_off   = item_off + 2 * static_cast<int>(sizeof(Item));
     static constexpr int n_bars    = 2 * kStages + 2 + 2 + 2 + 2;
     static constexpr int tmem_off  = bar_off + n_bars * 8;
@@ -716,8 +719,10 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
                 mbar_wait_spin(&q_empty[qb], qph ^ 1);
                 item_s[qb] = im;
                 if (im.n_tiles == 0) { mbar_arrive(&q_full[qb]); continue; }
-                mbar_arrive_expect_tx(&q_full[qb], kQBytes);
+                mbar_arrive_expect_tx(&q_full[qb], kQBytes + im.n_tiles * 32);
                 tma_load_2d(q_s + qb * kQBytes, &tmap, 0, im.q_row0, &q_full[qb]);
+                bulk_load_1d(smem + Cfg::pb_off + qb * Cfg::pb_bytes, args.pbits + static_cast<size_t>(im.t_row0 >> 8) * 8,
+                             im.n_tiles * 32, &q_full[qb]);
                 const uint8_t* ecode = args.ecode + static_cast<size_t>(im.t_row0 >> 8) * kECodeBytes;
                 for (int n = 0; n < im.n_tiles; ++n) {
                     mbar_wait_spin(&empty[stage], sphase ^ 1);
@@ -812,15 +817,16 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
                     if (T >= 0) {
                         const int base = (T >> 4) * kBlockT + (T & 15) * 16;
                         const int cs = (2 * hm1) * 256 + ((s == 0) == best_first ? 0 : 16);
-                        const int4* ckp = reinterpret_cast<const int4*>(args.ckey + im.t_row0 + base);
+                        uint32_t ps;                       // norm parity of the chunk's 16 columns, at bits 8..23
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ps) : "r"(smem_u32(smem + Cfg::pb_off) + qb * Cfg::pb_bytes + (base >> 3)));
+                        ps <<= 8;
 #pragma unroll
                         for (int part = 0; part < 4; ++part) {
                             const int4 v = lds128(sa + part * Cfg::part_stride);
-                            const int4 ck = __ldg(ckp + part);
-                            k[s * 16 + part * 4 + 0] = mad_key(v.x, args.neg512, cs) + ((ck.x & 256) + part * 4 + 0);
-                            k[s * 16 + part * 4 + 1] = mad_key(v.y, args.neg512, cs) + ((ck.y & 256) + part * 4 + 1);
-                            k[s * 16 + part * 4 + 2] = mad_key(v.z, args.neg512, cs) + ((ck.z & 256) + part * 4 + 2);
-                            k[s * 16 + part * 4 + 3] = mad_key(v.w, args.neg512, cs) + ((ck.w & 256) + part * 4 + 3);
+                            k[s * 16 + part * 4 + 0] = mad_key(v.x, args.neg512, cs) + (((ps >> (part * 4 + 0)) & 256) + part * 4 + 0);
+                            k[s * 16 + part * 4 + 1] = mad_key(v.y, args.neg512, cs) + (((ps >> (part * 4 + 1)) & 256) + part * 4 + 1);
+                            k[s * 16 + part * 4 + 2] = mad_key(v.z, args.neg512, cs) + (((ps >> (part * 4 + 2)) & 256) + part * 4 + 2);
+                            k[s * 16 + part * 4 + 3] = mad_key(v.w, args.neg512, cs) + (((ps >> (part * 4 + 3)) & 256) + part * 4 + 3);
                         }
                     } else {
 #pragma unroll
@@ -869,7 +875,7 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
 // One CTA of 256 threads per pair; pairs that share a train frame write identical bytes.
 __global__ void __launch_bounds__(256)
 match_prepare_kernel(const int32_t* ckey, const int32_t* row_off, const int32_t* n_kp, const int32_t* pair_t,
-                     int32_t* pair_hmax, int32_t* pair_flag, uint8_t* ecode, int32_t* fix_count) {
+                     int32_t* pair_hmax, int32_t* pair_flag, uint8_t* ecode, uint32_t* pbits, int32_t* fix_count) {
     __shared__ int s_max[8], s_min[8];
     const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (p == 0 && tid == 0) *fix_count = 0;
@@ -889,15 +895,19 @@ match_prepare_kernel(const int32_t* ckey, const int32_t* row_off, const int32_t*
     hmax = s_max[0]; hmin = s_min[0];
 #pragma unroll
     for (int w = 1; w < 8; ++w) { hmax = max(hmax, s_max[w]); hmin = min(hmin, s_min[w]); }
-    const bool wide = nt > 0 && hmax - hmin + 1 > kEMax;
+    // (frames above EVZ_MAX_KP would overflow the kernel's parity bitmap buffers: legacy kernel as well)
+    const bool wide = nt > 0 && (hmax - hmin + 1 > kEMax || nt > EVZ_MAX_KP);
     if (tid == 0) { pair_hmax[p] = hmax; pair_flag[p] = wide ? 1 : 0; }
     if (wide) return;
     const int n_tiles = (nt + kBlockT - 1) / kBlockT;
     for (int n = 0; n < n_tiles; ++n) {
         const int c = n * kBlockT + tid;
         uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const int ckv = c < nt ? ckey[base + c] : 0;
+        const unsigned par = __ballot_sync(0xffffffff, (ckv >> 8) & 1);
+        if (lane == 0) pbits[(static_cast<size_t>(base >> 8) + n) * 8 + warp] = par;
         if (c < nt) {
-            const int E = hmax + 1 - (ckey[base + c] >> 9);
+            const int E = hmax + 1 - (ckv >> 9);
             const int m = E / 255, r = E - 255 * m;
 #pragma unroll
             for (int k = 0; k < 30; ++k) {
@@ -1018,7 +1028,8 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
     // scratch: [counters 256 B][items A][items B][pair_hmax][pair_flag][ecode]
     const size_t items_bytes = evz_align_up(capacity * 8, 256), pair_bytes = evz_align_up(static_cast<size_t>(n_pairs) * 4, 256);
     const size_t fix_bytes = evz_align_up(capacity * 256 * 4, 256);          // every row of every item, at worst
-    const size_t ecode_off = evz_align_up(256 + 2 * items_bytes + 2 * pair_bytes + fix_bytes, 1024);
+    const size_t pbits_bytes = evz_align_up(static_cast<size_t>(total_rows) / 8, 256);     // one bit per store row
+    const size_t ecode_off = evz_align_up(256 + 2 * items_bytes + 2 * pair_bytes + fix_bytes + pbits_bytes, 1024);
     EVZ_REQUIRE(h, !vspace || capacity < (size_t(1) << 22), "too many work items for the V-space kernel (set EVZ_OPT_MATCH_VARIANT=5)");
     void* scr = nullptr;
     rc = evz_scratch(h, vspace ? ecode_off + static_cast<size_t>(total_rows) * 32 : 256 + items_bytes, &scr);
@@ -1026,7 +1037,7 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
     uint8_t* sb = static_cast<uint8_t*>(scr);
     int32_t* n_items = reinterpret_cast<int32_t*>(sb);
     int32_t* items = reinterpret_cast<int32_t*>(sb + 256);
-    evz::MatchArgs a{ckey, row_off, n_kp, pair_q, pair_t, out_off, items, n_items, top2_idx, top2_d2, -512, nullptr, nullptr, 256u,
+    evz::MatchArgs a{ckey, row_off, n_kp, pair_q, pair_t, out_off, items, n_items, top2_idx, top2_d2, -512, nullptr, nullptr, nullptr, 256u,
                      nullptr, nullptr, 0};
 #define EVZ_MATCH_LAUNCH(CH, EW)                                                                                         \
     do {                                                                                                                 \
@@ -1048,7 +1059,9 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
         a.fix_count = n_items + 32;
         a.fix_list = reinterpret_cast<int32_t*>(sb + 256 + 2 * items_bytes + 2 * pair_bytes);
         a.fix_capacity = static_cast<int>(capacity * 256);
-        evz::match_prepare_kernel<<<n_pairs, 256, 0, st>>>(ckey, row_off, n_kp, pair_t, pair_hmax, pair_flag, ecode, a.fix_count);
+        uint32_t* pbits = reinterpret_cast<uint32_t*>(sb + 256 + 2 * items_bytes + 2 * pair_bytes + fix_bytes);
+        a.pbits = pbits;
+        evz::match_prepare_kernel<<<n_pairs, 256, 0, st>>>(ckey, row_off, n_kp, pair_t, pair_hmax, pair_flag, ecode, pbits, a.fix_count);
         EVZ_LAUNCH_CHECK(h);
         evz::build_items_kernel<<<1, 1024, 0, st>>>(n_kp, pair_q, n_pairs, items, n_items, static_cast<int>(capacity), pair_flag, 0);
         evz::build_items_kernel<<<1, 1024, 0, st>>>(n_kp, pair_q, n_pairs, items_slow, n_items_slow, static_cast<int>(capacity), pair_flag, 1);

@@ -623,7 +623,7 @@ __device__ __forceinline__ void vchunk(const uint32_t* r, uint32_t tagc, uint32_
                  "@p2 st.shared.v4.b32 [%1+2*%22], {%14, %15, %16, %17};\n\t"
                  "@p2 st.shared.v4.b32 [%1+3*%22], {%18, %19, %20, %21};\n\t"
                  "selp.u32 %0, %5, %1, p1;\n\t}"
-                 : "=r"(nsec) : "r"(sec), "r"(cmk), "r"(M1), "r"(M2), "r"(alt),
+                 : "=&r"(nsec) : "r"(sec), "r"(cmk), "r"(M1), "r"(M2), "r"(alt),
                    "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
                    "n"(VCfg::part_stride) : "memory");
@@ -634,28 +634,33 @@ __device__ __forceinline__ void vchunk(const uint32_t* r, uint32_t tagc, uint32_
     M2 = max(M2, t);
 }
 
-// one accumulator row (256 columns): 4 batches of 64 columns, TMEM loads one batch ahead (a batch takes
-// longer to process than a TMEM load takes to arrive; with batches of 32 it does not); the accumulator is
+// keeps 16 registers allocated up to this point: the predicated stores of a chunk read them late, and a
+// temporary that the allocator placed on one of them would wait for those reads (write-after-read stall)
+__device__ __forceinline__ void keep_alive16(const uint32_t* r) {
+    asm volatile("" :: "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                       "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
+}
+
+// one accumulator row (256 columns): 8 batches of 32 columns, TMEM loads one batch ahead; the accumulator is
 // handed back to the MMA warp as soon as its last column is in registers
 __device__ __forceinline__ void drain_v(uint32_t taddr, uint32_t mul, uint32_t& M1, uint32_t& M2, uint32_t& M3,
                                         uint32_t& sec, uint32_t sum, uint64_t* acc_empty, int lane) {
-    uint32_t r[2][2][32];
-    tmem_ld_32x32b_x32(taddr, r[0][0]);
-    tmem_ld_32x32b_x32(taddr + 32, r[0][1]);
+    uint32_t r[2][32];
+    tmem_ld_32x32b_x32(taddr, r[0]);
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        tmem_ld_wait_dep(r[b & 1][0]);
-        tmem_ld_wait_dep(r[b & 1][1]);
-        if (b + 1 < 4) {
-            tmem_ld_32x32b_x32(taddr + (b + 1) * 64, r[(b + 1) & 1][0]);
-            tmem_ld_32x32b_x32(taddr + (b + 1) * 64 + 32, r[(b + 1) & 1][1]);
+    for (int b = 0; b < 8; ++b) {
+        tmem_ld_wait_dep(r[b & 1]);
+        if (b + 1 < 8) {
+            tmem_ld_32x32b_x32(taddr + (b + 1) * 32, r[(b + 1) & 1]);
         } else {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);
         }
-#pragma unroll
-        for (int c = 0; c < 4; ++c) vchunk(&r[b & 1][c >> 1][16 * (c & 1)], 254 - 4 * b - c, mul, M1, M2, M3, sec, sum);
+        vchunk(&r[b & 1][0], 254 - 2 * b, mul, M1, M2, M3, sec, sum);
+        vchunk(&r[b & 1][16], 253 - 2 * b, mul, M1, M2, M3, sec, sum);
+        keep_alive16(&r[b & 1][0]);
+        keep_alive16(&r[b & 1][16]);
     }
 }
 
@@ -725,6 +730,12 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
                              im.n_tiles * 32, &q_full[qb]);
                 const uint8_t* ecode = args.ecode + static_cast<size_t>(im.t_row0 >> 8) * kECodeBytes;
                 for (int n = 0; n < im.n_tiles; ++n) {
+                    // the ring is only kStages deep: pull the tile that will be loaded kStages iterations from now
+                    // into L2 already, so that its TMA load is an L2 hit
+                    if (n + kStages < im.n_tiles) {
+                        tma_prefetch_2d(&tmap, 0, im.t_row0 + (n + kStages) * kBlockT);
+                        bulk_prefetch_1d(ecode + static_cast<size_t>(n + kStages) * kECodeBytes, kECodeBytes);
+                    }
                     mbar_wait_spin(&empty[stage], sphase ^ 1);
                     mbar_arrive_expect_tx(&full[stage], kTileBytes + kECodeBytes);
                     tma_load_2d(t_s + stage * kTileBytes, &tmap, 0, im.t_row0 + n * kBlockT, &full[stage]);

@@ -2,13 +2,16 @@
 // with a fused distance / top-2 epilogue.  Replaces cv2 BFMatcher.knnMatch(q, t, 2)
 // (reference evenvizion/processing/matching.py:102-108).
 //
-// Work item = (pair, block of 256 query rows).  For every 256-row train tile the CTA issues
-//   acc[sub] (128 x 256, s32, TMEM) = Q[sub] (128 x 128 u8) . T (256 x 128 u8)^T     sub = 0, 1
-// as 4 x tcgen05.mma.kind::i8 (K = 32 each).  One train tile in shared memory feeds both query
-// sub-tiles, and the two 256-column accumulators double-buffer TMEM: the epilogue drains acc[0]
-// while the tensor core fills acc[1].
+// Two kernels share the TMA / tcgen05 front end (work item = (pair, block of 256 query rows); per 256-row
+// train tile one 128 x 256 accumulator per 128-row query sub-tile, K = 128 bytes = 4 x tcgen05.mma.kind::i8):
 //
-// Epilogue, per accumulator element (row r = query, column c = train):
+//  * match_top2_vkernel ("V-space", default; second half of this file): the train norm enters the accumulator
+//    through a fifth K block, so the epilogue is a max tree over raw accumulator values -- about half the
+//    instructions per output of the key-space epilogue.
+//  * match_top2_kernel ("key-space", this half; EVZ_OPT_MATCH_VARIANT 5 / 1 / 2 and the fallback for pairs
+//    whose train frame has a norm range the fifth K block cannot encode).
+//
+// Key-space epilogue, per accumulator element (row r = query, column c = train):
 //   key = ckey[c] - 512 * acc = ((||t_c||^2 - 2 q.t_c) << 8) | c      (one IMAD on the FMA pipe; the
 //   multiplier is a kernel argument so that ptxas cannot strength-reduce it onto the ALU pipe)
 // ckey[c] = (||t_c||^2 << 8) | (c & 255) comes from the frame store, INT32_MAX for padding rows;
@@ -30,10 +33,10 @@
 // The running best crosses tile boundaries as a sentinel key (V1 << 8, made distinct from every
 // real key of the thread's column range), so a later tile only wins with a strictly smaller distance.
 //
-// Warp roles (128 + 32 kEW threads, 1 CTA / SM, persistent over items):
+// Warp roles (128 + 256 threads, 1 CTA / SM, persistent over items):
 //   warp 0 : TMA producer (query block, train tiles, item descriptor ring)   warp 1 : MMA issuer
 //   warp 2 : TMEM allocator        warp 3 : ckey producer
-//   warps 4.. : kEW epilogue warps; warp w reads TMEM lanes 32*(w%4).. and the column group (w-4)/4
+//   warps 4-11 : epilogue; warp w reads TMEM lanes 32*(w%4).. and the column half (w-4)/4
 #include "evz_common.cuh"
 #include "evz_ptx.cuh"
 #include <climits>
@@ -554,8 +557,9 @@ __global__ void build_items_kernel(const int32_t* n_kp, const int32_t* pair_q, i
 //   =>  ||t_c||^2 - 2 q_r . t_c = 2 (hmax + 1 - V[r][c]) + (||t_c||^2 & 1)
 // hmax = max over the train frame of ||t||^2 >> 1.  A larger V is a strictly smaller distance; equal V
 // differ by the norm parity only.  E_c is a u8 x u8 dot product of the constant query-side vector
-// a = (255 x 30, 1, 0) with 32 code bytes per train row (match_prepare_kernel), good for
-// hmax - hmin < kEMax; pairs with a wider norm range go through the legacy kernel.
+// a = (255 x 30, 1, 0) with 32 code bytes per train row (match_prepare_kernel writes them, in the no-swizzle
+// core-matrix layout the MMA reads, plus one norm-parity bit per row), good for hmax - hmin < kEMax;
+// pairs with a wider norm range or more than EVZ_MAX_KP train rows go through the key-space kernel.
 //
 // Epilogue (8 warps; warps 4-7 drain accumulator 0 = query sub-tile 0, warps 8-11 accumulator 1; one query
 // row and all 256 columns of a tile per thread): every aligned chunk of 16 columns is reduced to its
@@ -563,11 +567,20 @@ __global__ void build_items_kernel(const int32_t* n_kp, const int32_t* pair_q, i
 // sorted top-3 of chunk keys is kept (5 min/max).  A chunk that beats the second-best key is saved raw
 // into the slot that holds the second-best chunk (4 predicated 128-bit stores); when it also beats the
 // best key the two slots swap roles.  At the end of the item the two slots hold the two best chunks:
-// their 32 columns are evaluated exactly (norm, parity, index), and the result is exact whenever the
-// second-best distance found is strictly below the bound 2 (hmax + 1 - V3) of every other column
-// (V3 = third chunk maximum).  Rows that cannot be certified (a value tie between the second and third
-// chunk: ~1e-3 of the rows on descriptor-like data, every row on degenerate data) are flagged and
-// recomputed by match_fixup_kernel.
+// their 32 columns are evaluated exactly (norm parity from the shared-memory bitmap, index), and the result
+// is exact whenever the second-best distance found is strictly below the bound 2 (hmax + 1 - V3) of every
+// other column (V3 = third chunk maximum).  Rows that cannot be certified (a value tie between the second
+// and third chunk: ~1e-3 of the rows on descriptor-like data, every row on degenerate data) are flagged
+// and recomputed by match_fixup_kernel (dp4a brute force, one CTA per row).
+//
+// Measured (B200, 2048 keypoints/frame, profiles/r01e_*): 1.8 warp instructions per 32 outputs against 3.3
+// in the key-space kernel; tensor pipe active 56 % (45 % algorithmic + the fifth K block), issue slots 45 %,
+// ALU pipe 57 %.  What bounds it now is the accumulator hand-off: a sub-tile's accumulator is drained by the
+// four warps of its group, one warp per scheduler, and one warp reads TMEM at ~61 B/clk (scripts/microbench/
+// tmem_bw.cu), so a 128 KB accumulator takes >= 525 clk to drain before its next MMA (640 clk) can start.
+// Variants that drain every accumulator with all eight warps (2 x the slot memory: needs a single query
+// buffer) or use four 128-column accumulators (N = 128 MMAs are shared-memory-bandwidth bound: 81 instead of
+// 64 clk) or chunks of 32 measured slower at this tile shape; see DESIGN.md.
 constexpr int kECodeBytes = kBlockT * 32;                 // fifth K block of one train tile
 constexpr int kEMax       = 255 * (30 * 255) + 254;       // largest representable E_c
 constexpr int kFlagged    = -2;                           // top2_idx[row][0] of a row left to the fix-up kernel

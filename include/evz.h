@@ -79,9 +79,10 @@ int         evz_sm_count(const evz_handle* h);
 
 /* debugging / A-B options; results are identical for every setting, only the route differs */
 #define EVZ_OPT_RANSAC_EXACT   1  /* 1: score every hypothesis x match with the exactly-rounded formula (no fused fast path) */
-#define EVZ_OPT_MATCH_VARIANT  2  /* match epilogue: 0 default (chunk-8 minima + saved best chunk, 8 epilogue warps);
-                                     1 exact top-2 per element (8 warps); 2 chunk 16 (8 warps); 3 chunk 8 (16 warps);
-                                     4 exact top-2 per element (16 warps) */
+#define EVZ_OPT_MATCH_VARIANT  2  /* match kernel: 0 default ("V-space": the train norm enters the accumulator through a
+                                     fifth K block, max-tree epilogue, exact resolution from two saved chunks + fix-up);
+                                     key-space kernel (distance/index keys formed per element): 5 chunk-8 minima + saved
+                                     best chunk, 1 exact top-2 per element, 2 chunk-16 minima */
 #define EVZ_OPT_RANSAC_NO_PRUNE 3  /* 1: score every valid hypothesis even after one of them counted all matches as inliers
                                      (default 0: hypotheses that can no longer win the (count desc, index asc) arg-max are skipped) */
 int         evz_set_option(evz_handle* h, int option, int value);
@@ -106,6 +107,8 @@ int evz_ingest(evz_handle* h, const void* raw_desc, int raw_is_f32, int d,
  * cv2.DescriptorMatcher_create("BruteForce").knnMatch(q, t, 2) at matching.py:102-108.
  * u8 x u8 -> s32 tcgen05.mma (kind::i8), TMA-staged tiles, TMEM accumulators, fused
  * ||a||^2 + ||b||^2 - 2ab / top-2 epilogue.  Ties resolve to the lowest train index.
+ * Uses handle scratch of about 33 bytes per store row + 1 KB per 256-row query block
+ * (fifth-K-block codes, norm parity bitmap, work items, fix-up list).
  *   top2_idx DEV int32 [rows][2]  train keypoint index (frame-local), -1 when absent
  *   top2_d2  DEV int32 [rows][2]  exact squared L2 distance,          -1 when absent
  * (knnMatch's DMatch.distance is sqrtf((float)d2), bit for bit.)

@@ -1,6 +1,6 @@
 """Drop-in for `evenvizion.processing` (reference evenvizion/processing/__init__.py): same module
 and function names, arithmetic on the GPU through libevz.so."""
-__all__ = ['constants', 'frame_processing', 'fixed_coordinate_system', 'matching', 'utils', 'video_processing']
+__all__ = ['constants', 'frame_processing', 'fixed_coordinate_system', 'formats', 'matching', 'utils', 'video_processing']
 
 from .constants import *                      # noqa: F401,F403
 from .frame_processing import FrameProcessing, resize           # noqa: F401
@@ -11,3 +11,4 @@ from .utils import (HomographyException, remove_double_matching, homography_tran
                     superposition_dict, are_infinity_coordinates, read_json_with_coordinates,
                     get_largest_group_points, find_point_displacement, compute_homography)
 from .video_processing import get_homography_dict, geometry_from_features, read_and_describe       # noqa: F401
+from .formats import dump_homography_dict, load_homography_arrays, dump_coordinates, load_coordinates_arrays   # noqa: F401

@@ -149,3 +149,52 @@ def test_two_rank_gloo_all_gather_seeding(policy):
         assert p.exitcode == 0
     assert sorted(r for r, _ in res) == [0, 1]
     assert max(e for _, e in res) < 1e-9
+
+
+def test_streaming_json_writers_match_json_dump(tmp_path, bundled):
+    """the streaming writers emit exactly the bytes json.dump produces for the reference's dicts,
+    and the array readers invert them (incl. the bundled dict_with_homography_matrix.json)."""
+    import io
+    import json
+    from evenvizion_b200.processing import formats
+    rng = np.random.default_rng(4)
+    P = 9000                                                    # more than one write chunk
+    H = rng.normal(size=(P, 3, 3)) * np.array([1.0, 1e-3, 1e2])[None, :, None]
+    H[:, 2, 2] = 1.0
+    H[5] = [[1, 0, 0], [0, 1, 0], [0, 0, 1]]
+    valid = np.ones(P, bool)
+    valid[[3, 4000]] = False
+    ref = {str(k + 2): {"H": (H[k].tolist() if valid[k] else None)} for k in range(P)}
+    ref["resize_info"] = {"h": 224, "w": 400}
+    buf = io.StringIO()
+    formats.dump_homography_dict(buf, H, {"h": 224, "w": 400}, valid=valid)
+    assert buf.getvalue() == json.dumps(ref)
+    path = tmp_path / "dict_with_homography_matrix.json"
+    formats.dump_homography_dict(path, H, {"h": 224, "w": 400}, valid=valid)
+    frames, H2, v2, ri = formats.load_homography_arrays(path)
+    assert np.array_equal(frames, np.arange(2, P + 2)) and np.array_equal(v2, valid) and ri == {"h": 224, "w": 400}
+    assert np.array_equal(H2[valid], H[valid]) and np.isnan(H2[~valid]).all()
+    with pytest.raises(ValueError):
+        formats.load_homography_arrays(io.StringIO('{"2": {"H": null}}'))
+    # the bundled reference file round-trips byte for byte
+    hd = bundled["homography_dict"]
+    keys = sorted(int(k) for k in hd)
+    Hb = np.array([hd[str(k)]["H"] for k in keys])
+    out = io.StringIO()
+    formats.dump_homography_dict(out, Hb, bundled["resize_info"], first_frame=keys[0])
+    assert out.getvalue() == json.dumps({**{str(k): hd[str(k)] for k in keys}, "resize_info": bundled["resize_info"]})
+    # coordinates
+    counts = rng.integers(0, 9, 500)
+    xy = np.round(rng.normal(size=(int(counts.sum()), 2)) * 300, 2)
+    extra = [{"x1": 0.0, "y1": 0.0, "id": int(i)} for i in range(len(xy))]
+    refc, j = {}, 0
+    for fr, n in enumerate(counts, start=1):
+        refc[str(fr)] = []
+        for _ in range(n):
+            refc[str(fr)].append({"x1": float(xy[j, 0]), "y1": float(xy[j, 1]), "id": j})
+            j += 1
+    out = io.StringIO()
+    formats.dump_coordinates(out, np.arange(1, 501), counts, xy, extra=extra)
+    assert out.getvalue() == json.dumps(refc)
+    fr2, c2, xy2 = formats.load_coordinates_arrays(io.StringIO(out.getvalue()))
+    assert np.array_equal(fr2, np.arange(1, 501)) and np.array_equal(c2, counts) and np.array_equal(xy2, xy)

@@ -26,6 +26,7 @@ SIGNATURES = {
     "evz_last_error": [_p],
     "evz_sm_count": [_p],
     "evz_set_option": [_p, _i, _i],
+    "evz_match_kernel_ms": [_p, _i, C.POINTER(C.c_float)],
     "evz_ingest": [_p, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
     "evz_match_top2": [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _i, _p, _p, _p],
     "evz_filter_matches": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _d, _i, _p, _p, _p, _p, _p, _p, _p],

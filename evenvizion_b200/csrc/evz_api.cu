@@ -45,6 +45,8 @@ extern "C" int evz_create(int device, evz_handle** out) {
 extern "C" void evz_destroy(evz_handle* h) {
     if (!h) return;
     if (h->scratch) cudaFree(h->scratch);
+    if (h->match_ev_made)
+        for (auto& pr : h->match_ev) { cudaEventDestroy(pr[0]); cudaEventDestroy(pr[1]); }
     delete h;
 }
 
@@ -58,8 +60,18 @@ extern "C" int evz_set_option(evz_handle* h, int option, int value) {
         case EVZ_OPT_RANSAC_EXACT: h->opt_ransac_exact = value; return EVZ_OK;
         case EVZ_OPT_MATCH_VARIANT: h->opt_match_variant = value; return EVZ_OK;
         case EVZ_OPT_RANSAC_NO_PRUNE: h->opt_ransac_no_prune = value; return EVZ_OK;
+        case EVZ_OPT_TIME_MATCH: h->opt_time_match = value; return EVZ_OK;
         default: EVZ_SET_ERR(h, "evz_set_option: unknown option %d", option); return EVZ_E_ARG;
     }
+}
+
+extern "C" int evz_match_kernel_ms(evz_handle* h, int k, float* ms) {
+    if (!h || !ms) return EVZ_E_ARG;
+    EVZ_REQUIRE(h, h->match_ev_made && k >= 0 && k < 16 && static_cast<unsigned long long>(k) < h->match_calls,
+                "no timing record (set EVZ_OPT_TIME_MATCH and call evz_match_top2 first)");
+    const auto& pr = h->match_ev[(h->match_calls - 1 - k) & 15];
+    EVZ_CUDA_CHECK(h, cudaEventElapsedTime(ms, pr[0], pr[1]));
+    return EVZ_OK;
 }
 
 int evz_scratch(evz_handle* h, size_t bytes, void** out) {

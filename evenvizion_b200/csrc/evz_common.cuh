@@ -29,6 +29,11 @@ struct evz_handle {
     int opt_ransac_exact = 0;
     int opt_ransac_no_prune = 0;
     int opt_match_variant = 0;
+    int opt_time_match = 0;
+    // EVZ_OPT_TIME_MATCH: ring of event pairs around the main match kernel
+    cudaEvent_t match_ev[16][2] = {};
+    bool match_ev_made = false;
+    unsigned long long match_calls = 0;
 };
 
 #define EVZ_SET_ERR(h, ...) do { if (h) snprintf((h)->err, sizeof((h)->err), __VA_ARGS__); } while (0)

@@ -1097,8 +1097,18 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
             v_attr_set = true;
         }
+        cudaEvent_t* tev = nullptr;
+        if (h->opt_time_match) {
+            if (!h->match_ev_made) {
+                for (auto& pr : h->match_ev) { EVZ_CUDA_CHECK(h, cudaEventCreate(&pr[0])); EVZ_CUDA_CHECK(h, cudaEventCreate(&pr[1])); }
+                h->match_ev_made = true;
+            }
+            tev = h->match_ev[h->match_calls++ & 15];
+            EVZ_CUDA_CHECK(h, cudaEventRecord(tev[0], st));
+        }
         evz::match_top2_vkernel<<<h->sm_count, evz::VCfg::threads, evz::VCfg::smem_bytes, st>>>(h->tmap, a);
         EVZ_LAUNCH_CHECK(h);
+        if (tev) EVZ_CUDA_CHECK(h, cudaEventRecord(tev[1], st));
         evz::match_fixup_kernel<<<h->sm_count * 8, 128, 0, st>>>(desc, a);
         EVZ_LAUNCH_CHECK(h);
         // pairs whose train frame has a norm range the fifth K block cannot encode: legacy kernel (normally no items)

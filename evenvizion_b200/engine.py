@@ -107,6 +107,13 @@ class GeometryEngine:
         """EVZ_OPT_* switches of include/evz.h (A/B routes with identical results)."""
         self._check(self.lib.evz_set_option(self.h, int(option), int(value)))
 
+    def match_kernel_ms(self, k=0):
+        """CUDA-event time of the main match kernel of the k-th most recent `match` call (EVZ_OPT_TIME_MATCH = option 4
+        must be on; synchronise the stream first)."""
+        ms = C.c_float(0.0)
+        self._check(self.lib.evz_match_kernel_ms(self.h, int(k), C.byref(ms)))
+        return float(ms.value)
+
     # ------------------------------------------------------------------ helpers
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)

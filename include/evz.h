@@ -85,7 +85,12 @@ int         evz_sm_count(const evz_handle* h);
                                      best chunk, 1 exact top-2 per element, 2 chunk-16 minima */
 #define EVZ_OPT_RANSAC_NO_PRUNE 3  /* 1: score every valid hypothesis even after one of them counted all matches as inliers
                                      (default 0: hypotheses that can no longer win the (count desc, index asc) arg-max are skipped) */
+#define EVZ_OPT_TIME_MATCH     4  /* 1: evz_match_top2 brackets its main kernel with CUDA events on the caller's stream (a ring of
+                                     16 pairs, one per call); read them with evz_match_kernel_ms after synchronising */
 int         evz_set_option(evz_handle* h, int option, int value);
+/* elapsed time of the main match kernel of the k-th most recent evz_match_top2 call (k = 0: the last one), for the
+ * roofline line of bench.py.  The stream must have been synchronised; returns EVZ_E_ARG when no such record exists. */
+int         evz_match_kernel_ms(evz_handle* h, int k, float* ms);
 
 /* ---- ingest: the step before the path.  Replaces the implicit
  * np.float32 -> cv::Mat conversion inside knnMatch (matching.py:108) and prepares

@@ -517,7 +517,7 @@ __device__ __forceinline__ void score_slots(const FhArgs& a, const float4* pts, 
 }
 
 // dynamic shared memory of the scoring kernel: float4 pts[max_cnt] | u16 vlist, slist, lo_s, hi_s [n_hyp] each
-__global__ void __launch_bounds__(kRsThreads, 3)
+__global__ void __launch_bounds__(kRsThreads, 4)
 ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __restrict__ phase) {
     extern __shared__ __align__(16) uint8_t fh_smem[];
     float4* pts = reinterpret_cast<float4*>(fh_smem);

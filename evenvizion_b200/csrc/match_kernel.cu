@@ -575,16 +575,22 @@ __global__ void build_items_kernel(const int32_t* n_kp, const int32_t* pair_q, i
 //
 // Measured (B200, 2048 keypoints/frame, profiles/r01e_*): 1.8 warp instructions per 32 outputs against 3.3
 // in the key-space kernel; tensor pipe active 56 % (45 % algorithmic + the fifth K block), issue slots 45 %,
-// ALU pipe 57 %.  What bounds it now is the accumulator hand-off: a sub-tile's accumulator is drained by the
-// four warps of its group, one warp per scheduler, and one warp reads TMEM at ~61 B/clk (scripts/microbench/
-// tmem_bw.cu), so a 128 KB accumulator takes >= 525 clk to drain before its next MMA (640 clk) can start.
-// Variants that drain every accumulator with all eight warps (2 x the slot memory: needs a single query
-// buffer) or use four 128-column accumulators (N = 128 MMAs are shared-memory-bandwidth bound: 81 instead of
-// 64 clk) or chunks of 32 measured slower at this tile shape; see DESIGN.md.
+// ALU pipe 57 %.  What bounds it now is the SHARED-MEMORY DATA PIPE (one 128-byte wavefront per clock): the
+// tensor core's operand fetch takes 41 % of it (10 MMAs x 12 KB per tile: the 128-row A sub-tile is re-read
+// for every MMA), the predicated chunk saves 36 % (1.5 wavefronts per STS.128: the few active lanes are
+// spread over the four quarter-warp phases), other LSU traffic 10 %, and the TMA writes of the incoming
+// tiles come on top -- about 2 170 wavefronts per tile against a measured tile time of 2 100-2 300 clk.
+// That is why variants that only cut instructions (chunks of 32), only shorten the accumulator hand-off (all
+// eight warps per accumulator, 16 epilogue warps), poll barriers from all threads or use N = 128 MMAs (more
+// operand fetch per MAC) measured equal or slower; chunks of 8 (kVC) halve the saved bytes but add
+// instructions: faster at 1024 keypoints, slower at 8192.  See DESIGN.md.
 constexpr int kECodeBytes = kBlockT * 32;                 // fifth K block of one train tile
 constexpr int kEMax       = 255 * (30 * 255) + 254;       // largest representable E_c
 constexpr int kFlagged    = -2;                           // top2_idx[row][0] of a row left to the fix-up kernel
 
+constexpr int kVC   = 16;                // columns per chunk of the V-space epilogue (8 or 16)
+constexpr int kVCps = kBlockT / kVC;     // chunks per tile
+constexpr int kVClog = kVC == 8 ? 5 : 4; // log2(kVCps)
 struct VCfg {
     static constexpr int threads   = 384;
     static constexpr int q_off     = 0;                                // 2 x 32 KB
@@ -593,7 +599,7 @@ struct VCfg {
     static constexpr int a_off     = e_off + kStages * kECodeBytes;    // 4 KB: query-side fifth K block
     static constexpr int slot_off  = a_off + 128 * 32;                 // [slot 2][part 4][row 256] x 16 B
     static constexpr int part_stride = 256 * 16;
-    static constexpr int slot_stride = 4 * part_stride;
+    static constexpr int slot_stride = (kVC / 4) * part_stride;
     static constexpr int pb_bytes  = (EVZ_MAX_KP / kBlockT) * 32;      // norm parity bitmap of one train frame
     static constexpr int pb_off    = slot_off + 2 * slot_stride;       // 2 x pb_bytes, alternating per item
     static constexpr int item_off  = pb_off + 2 * pb_bytes;
@@ -616,30 +622,47 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr_bytes, uin
     return d;
 }
 
-// one chunk of 16 raw accumulator values: chunk key, sorted top-3 update, predicated save
+// one chunk of kVC raw accumulator values: chunk key, sorted top-3 update, predicated save
 __device__ __forceinline__ void vchunk(const uint32_t* r, uint32_t tagc, uint32_t mul, uint32_t& M1, uint32_t& M2,
                                        uint32_t& M3, uint32_t& sec, uint32_t sum) {
-    const uint32_t a = __vimax3_u32(r[0], r[1], r[2]), b = __vimax3_u32(r[3], r[4], r[5]), c = __vimax3_u32(r[6], r[7], r[8]);
-    const uint32_t d = __vimax3_u32(r[9], r[10], r[11]), e = __vimax3_u32(r[12], r[13], r[14]);
-    const uint32_t cm = max(__vimax3_u32(a, b, c), __vimax3_u32(d, e, r[15]));
+    uint32_t cm;
+    if (kVC == 16) {
+        const uint32_t a = __vimax3_u32(r[0], r[1], r[2]), b = __vimax3_u32(r[3], r[4], r[5]), c = __vimax3_u32(r[6], r[7], r[8]);
+        const uint32_t d = __vimax3_u32(r[9], r[10], r[11]), e = __vimax3_u32(r[12], r[13], r[14]);
+        cm = max(__vimax3_u32(a, b, c), __vimax3_u32(d, e, r[15]));
+    } else {
+        cm = __vimax3_u32(__vimax3_u32(r[0], r[1], r[2]), __vimax3_u32(r[3], r[4], r[5]), max(r[6], r[7]));
+    }
     uint32_t cmk;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(cmk) : "r"(cm), "r"(mul), "r"(tagc));
-    // the next store address goes to a fresh register: overwriting `sec` in place would wait for the four
-    // stores to have read it (write-after-read on the short scoreboard, ~35 clk per chunk)
+    // the next store address goes to a different register (early clobber): overwriting `sec` in place would wait
+    // for the stores to have read it (write-after-read on the short scoreboard, ~35 clk per chunk)
     const uint32_t alt = sum - sec;
     uint32_t nsec;
-    asm volatile("{\n\t.reg .pred p1, p2;\n\t"
-                 "setp.gt.u32 p2, %2, %4;\n\t"
-                 "setp.gt.u32 p1, %2, %3;\n\t"
-                 "@p2 st.shared.v4.b32 [%1], {%6, %7, %8, %9};\n\t"
-                 "@p2 st.shared.v4.b32 [%1+%22], {%10, %11, %12, %13};\n\t"
-                 "@p2 st.shared.v4.b32 [%1+2*%22], {%14, %15, %16, %17};\n\t"
-                 "@p2 st.shared.v4.b32 [%1+3*%22], {%18, %19, %20, %21};\n\t"
-                 "selp.u32 %0, %5, %1, p1;\n\t}"
-                 : "=&r"(nsec) : "r"(sec), "r"(cmk), "r"(M1), "r"(M2), "r"(alt),
-                   "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-                   "n"(VCfg::part_stride) : "memory");
+    if (kVC == 16) {
+        asm volatile("{\n\t.reg .pred p1, p2;\n\t"
+                     "setp.gt.u32 p2, %2, %4;\n\t"
+                     "setp.gt.u32 p1, %2, %3;\n\t"
+                     "@p2 st.shared.v4.b32 [%1], {%6, %7, %8, %9};\n\t"
+                     "@p2 st.shared.v4.b32 [%1+%22], {%10, %11, %12, %13};\n\t"
+                     "@p2 st.shared.v4.b32 [%1+2*%22], {%14, %15, %16, %17};\n\t"
+                     "@p2 st.shared.v4.b32 [%1+3*%22], {%18, %19, %20, %21};\n\t"
+                     "selp.u32 %0, %5, %1, p1;\n\t}"
+                     : "=&r"(nsec) : "r"(sec), "r"(cmk), "r"(M1), "r"(M2), "r"(alt),
+                       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                       "r"(r[8 % kVC]), "r"(r[9 % kVC]), "r"(r[10 % kVC]), "r"(r[11 % kVC]), "r"(r[12 % kVC]), "r"(r[13 % kVC]),
+                       "r"(r[14 % kVC]), "r"(r[15 % kVC]), "n"(VCfg::part_stride) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p1, p2;\n\t"
+                     "setp.gt.u32 p2, %2, %4;\n\t"
+                     "setp.gt.u32 p1, %2, %3;\n\t"
+                     "@p2 st.shared.v4.b32 [%1], {%6, %7, %8, %9};\n\t"
+                     "@p2 st.shared.v4.b32 [%1+%14], {%10, %11, %12, %13};\n\t"
+                     "selp.u32 %0, %5, %1, p1;\n\t}"
+                     : "=&r"(nsec) : "r"(sec), "r"(cmk), "r"(M1), "r"(M2), "r"(alt),
+                       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                       "n"(VCfg::part_stride) : "memory");
+    }
     sec = nsec;
     const uint32_t t = min(M1, cmk), u = __vimin3_u32(M1, M2, cmk);
     M1 = max(M1, cmk);
@@ -670,8 +693,8 @@ __device__ __forceinline__ void drain_v(uint32_t taddr, uint32_t mul, uint32_t& 
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);
         }
-        vchunk(&r[b & 1][0], 254 - 2 * b, mul, M1, M2, M3, sec, sum);
-        vchunk(&r[b & 1][16], 253 - 2 * b, mul, M1, M2, M3, sec, sum);
+#pragma unroll
+        for (int c = 0; c < 32 / kVC; ++c) vchunk(&r[b & 1][kVC * c], 254 - (32 / kVC) * b - c, mul, M1, M2, M3, sec, sum);
         keep_alive16(&r[b & 1][0]);
         keep_alive16(&r[b & 1][16]);
     }
@@ -823,8 +846,8 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
                     tc_fence_after();
                     drain_v(taddr, args.mul256, M1, M2, M3, sec, sum, &acc_empty[grp], lane);
                     ++g;
-                    const int nTb = M1 == o1 ? Tb : n * 16 + 254 - static_cast<int>(M1 & 255u);
-                    Ts = (M1 != o1 && M2 == o1) ? Tb : (M2 == o2 ? Ts : n * 16 + 254 - static_cast<int>(M2 & 255u));
+                    const int nTb = M1 == o1 ? Tb : n * kVCps + 254 - static_cast<int>(M1 & 255u);
+                    Ts = (M1 != o1 && M2 == o1) ? Tb : (M2 == o2 ? Ts : n * kVCps + 254 - static_cast<int>(M2 & 255u));
                     Tb = nTb;
                 }
                 // exact evaluation of the two saved chunks: ||t||^2 - 2 q.t = 2 (hmax + 1 - V) + parity, packed
@@ -833,37 +856,38 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
                 // columns have V = 0, i.e. a distance above every real column: they sort last by themselves.
                 const int hm1 = im.pad + 1;
                 const bool best_first = Ts < 0 || Tb < Ts;
-                int k[32];
+                int k[2 * kVC];
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     const int T = s == 0 ? Tb : Ts;
                     const uint32_t sa = s == 0 ? sum - sec : sec;
                     if (T >= 0) {
-                        const int base = (T >> 4) * kBlockT + (T & 15) * 16;
-                        const int cs = (2 * hm1) * 256 + ((s == 0) == best_first ? 0 : 16);
-                        uint32_t ps;                       // norm parity of the chunk's 16 columns, at bits 8..23
-                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ps) : "r"(smem_u32(smem + Cfg::pb_off) + qb * Cfg::pb_bytes + (base >> 3)));
+                        const int base = (T >> kVClog) * kBlockT + (T & (kVCps - 1)) * kVC;
+                        const int cs = (2 * hm1) * 256 + ((s == 0) == best_first ? 0 : kVC);
+                        uint32_t ps;                       // norm parity of the chunk's columns, moved to bits 8..
+                        if (kVC == 16) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ps) : "r"(smem_u32(smem + Cfg::pb_off) + qb * Cfg::pb_bytes + (base >> 3)));
+                        else           asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ps) : "r"(smem_u32(smem + Cfg::pb_off) + qb * Cfg::pb_bytes + (base >> 3)));
                         ps <<= 8;
 #pragma unroll
-                        for (int part = 0; part < 4; ++part) {
+                        for (int part = 0; part < kVC / 4; ++part) {
                             const int4 v = lds128(sa + part * Cfg::part_stride);
-                            k[s * 16 + part * 4 + 0] = mad_key(v.x, args.neg512, cs) + (((ps >> (part * 4 + 0)) & 256) + part * 4 + 0);
-                            k[s * 16 + part * 4 + 1] = mad_key(v.y, args.neg512, cs) + (((ps >> (part * 4 + 1)) & 256) + part * 4 + 1);
-                            k[s * 16 + part * 4 + 2] = mad_key(v.z, args.neg512, cs) + (((ps >> (part * 4 + 2)) & 256) + part * 4 + 2);
-                            k[s * 16 + part * 4 + 3] = mad_key(v.w, args.neg512, cs) + (((ps >> (part * 4 + 3)) & 256) + part * 4 + 3);
+                            k[s * kVC + part * 4 + 0] = mad_key(v.x, args.neg512, cs) + (((ps >> (part * 4 + 0)) & 256) + part * 4 + 0);
+                            k[s * kVC + part * 4 + 1] = mad_key(v.y, args.neg512, cs) + (((ps >> (part * 4 + 1)) & 256) + part * 4 + 1);
+                            k[s * kVC + part * 4 + 2] = mad_key(v.z, args.neg512, cs) + (((ps >> (part * 4 + 2)) & 256) + part * 4 + 2);
+                            k[s * kVC + part * 4 + 3] = mad_key(v.w, args.neg512, cs) + (((ps >> (part * 4 + 3)) & 256) + part * 4 + 3);
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) k[s * 16 + i] = INT_MAX;
+                        for (int i = 0; i < kVC; ++i) k[s * kVC + i] = INT_MAX;
                     }
                 }
                 int m1 = INT_MAX, m2 = INT_MAX;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) top2_pair(k[2 * i], k[2 * i + 1], m1, m2);
-                const int base_b = Tb >= 0 ? (Tb >> 4) * kBlockT + (Tb & 15) * 16 : 0;
-                const int base_s = Ts >= 0 ? (Ts >> 4) * kBlockT + (Ts & 15) * 16 : 0;
+                for (int i = 0; i < kVC; ++i) top2_pair(k[2 * i], k[2 * i + 1], m1, m2);
+                const int base_b = Tb >= 0 ? (Tb >> kVClog) * kBlockT + (Tb & (kVCps - 1)) * kVC : 0;
+                const int base_s = Ts >= 0 ? (Ts >> kVClog) * kBlockT + (Ts & (kVCps - 1)) * kVC : 0;
                 const int base_lo = best_first ? base_b : base_s, base_hi = best_first ? base_s : base_b;
-                const int c1 = ((m1 & 16) ? base_hi : base_lo) + (m1 & 15), c2 = ((m2 & 16) ? base_hi : base_lo) + (m2 & 15);
+                const int c1 = ((m1 & kVC) ? base_hi : base_lo) + (m1 & (kVC - 1)), c2 = ((m2 & kVC) ? base_hi : base_lo) + (m2 & (kVC - 1));
                 const int I1 = (m1 != INT_MAX && c1 < im.nt) ? c1 : -1, I2 = (m2 != INT_MAX && c2 < im.nt) ? c2 : -1;
                 const int V1 = m1 >> 8, V2 = m2 >> 8;
                 // every column outside the two slots has V <= V3, i.e. ||t||^2 - 2 q.t >= 2 (hmax + 1 - V3)

@@ -247,3 +247,36 @@ def test_match_wide_norm_range_falls_back(engine):
     r = engine.match(st, pq, pt)
     for p, (q, t) in enumerate(zip(pq, pt)):
         _check_pair(engine, st, r, p, frames, q, t)
+
+
+def test_match_largest_frames(engine):
+    """Frames of EVZ_MAX_KP = 12 288 keypoints (48 tiles per item: the parity bitmap buffers of the V-space kernel
+    are exactly full) next to a small frame, against an exact f32 GEMM on the device."""
+    rng = np.random.default_rng(77)
+    counts = [12288, 12288, 300, 4100]
+    tot = sum(counts)
+    base = rng.integers(0, 256, (6000, 128)).astype(np.uint8)
+    sel = rng.integers(0, len(base), tot)
+    desc = np.clip(base[sel].astype(np.int32) + rng.integers(-2, 3, (tot, 128)), 0, 255).astype(np.uint8)
+    coords = rng.random((tot, 2)).astype(np.float32)
+    st = engine.ingest(desc, coords, counts)
+    dd = torch.from_numpy(desc).cuda().float()
+    offs = np.r_[0, np.cumsum(counts)]
+    outs = {}
+    pq, pt = [1, 2, 3], [0, 1, 2]
+    for v in (0, 5):
+        engine.set_option(2, v)
+        outs[v] = engine.match(st, pq, pt)
+    engine.set_option(2, 0)
+    torch.cuda.synchronize()
+    for p, (q, t) in enumerate(zip(pq, pt)):
+        nq, nt = counts[q], counts[t]
+        ro = int(st.row_off_h[q])
+        Q, T = dd[offs[q]:offs[q] + nq], dd[offs[t]:offs[t] + nt]
+        d2 = (Q * Q).sum(1)[:, None] + (T * T).sum(1)[None, :] - 2 * (Q @ T.T)
+        key = d2.double() * 16384 + torch.arange(nt, device="cuda", dtype=torch.float64)[None, :]
+        top = torch.topk(key, 2, dim=1, largest=False).values
+        idx = (top % 16384).long(); val = torch.div(top, 16384, rounding_mode="floor").long()
+        for v in (0, 5):
+            assert torch.equal(outs[v].top2_idx[ro:ro + nq].long(), idx), (v, p)
+            assert torch.equal(outs[v].top2_d2[ro:ro + nq].long(), val), (v, p)

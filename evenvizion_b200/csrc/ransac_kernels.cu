@@ -182,24 +182,29 @@ __device__ __forceinline__ void ldl8_solve(const Ldl8& f, const double (&b)[8], 
 //   sums[18..20] Q  = sum (xi^2+yi^2) p2 p2^T                         : 00 01 11
 //   sums[21..23] sum p rx, [24..26] sum p ry, [27..28] sum -(xi rx + yi ry) p2
 //   sums[29] S = sum r^2, sums[30] = max |r|
+// (explicit fma(): this file is compiled with --fmad=false for the bit-exact kernels, but the refit only has
+// to reach the same optimum -- shared products and fused accumulation halve its f64 instruction count)
 __device__ __forceinline__ void lm_point(const double* h, const float4 pt, double* s) {
     const double Mx = pt.x, My = pt.y;
-    double ww = h[6] * Mx + h[7] * My + 1.0;
+    double ww = fma(h[6], Mx, fma(h[7], My, 1.0));
     ww = fabs(ww) > DBL_EPSILON ? 1.0 / ww : 0.0;
-    const double xi = (h[0] * Mx + h[1] * My + h[2]) * ww;
-    const double yi = (h[3] * Mx + h[4] * My + h[5]) * ww;
+    const double xi = fma(h[0], Mx, fma(h[1], My, h[2])) * ww;
+    const double yi = fma(h[3], Mx, fma(h[4], My, h[5])) * ww;
     const double rx = xi - pt.z, ry = yi - pt.w;
     const double p0 = Mx * ww, p1 = My * ww, p2 = ww;
-    s[0] += p0 * p0; s[1] += p0 * p1; s[2] += p0 * p2; s[3] += p1 * p1; s[4] += p1 * p2; s[5] += p2 * p2;
-    s[6] -= xi * p0 * p0; s[7] -= xi * p0 * p1; s[8] -= xi * p1 * p0; s[9] -= xi * p1 * p1; s[10] -= xi * p2 * p0; s[11] -= xi * p2 * p1;
-    s[12] -= yi * p0 * p0; s[13] -= yi * p0 * p1; s[14] -= yi * p1 * p0; s[15] -= yi * p1 * p1; s[16] -= yi * p2 * p0; s[17] -= yi * p2 * p1;
-    const double e = xi * xi + yi * yi;
-    s[18] += e * p0 * p0; s[19] += e * p0 * p1; s[20] += e * p1 * p1;
-    s[21] += p0 * rx; s[22] += p1 * rx; s[23] += p2 * rx;
-    s[24] += p0 * ry; s[25] += p1 * ry; s[26] += p2 * ry;
-    const double g = xi * rx + yi * ry;
-    s[27] -= g * p0; s[28] -= g * p1;
-    s[29] += rx * rx + ry * ry;
+    const double p00 = p0 * p0, p01 = p0 * p1, p02 = p0 * p2, p11 = p1 * p1, p12 = p1 * p2, p22 = p2 * p2;
+    s[0] += p00; s[1] += p01; s[2] += p02; s[3] += p11; s[4] += p12; s[5] += p22;
+    s[6] = fma(-xi, p00, s[6]); s[7] = fma(-xi, p01, s[7]); s[8] = fma(-xi, p01, s[8]); s[9] = fma(-xi, p11, s[9]);
+    s[10] = fma(-xi, p02, s[10]); s[11] = fma(-xi, p12, s[11]);
+    s[12] = fma(-yi, p00, s[12]); s[13] = fma(-yi, p01, s[13]); s[14] = fma(-yi, p01, s[14]); s[15] = fma(-yi, p11, s[15]);
+    s[16] = fma(-yi, p02, s[16]); s[17] = fma(-yi, p12, s[17]);
+    const double e = fma(xi, xi, yi * yi);
+    s[18] = fma(e, p00, s[18]); s[19] = fma(e, p01, s[19]); s[20] = fma(e, p11, s[20]);
+    s[21] = fma(p0, rx, s[21]); s[22] = fma(p1, rx, s[22]); s[23] = fma(p2, rx, s[23]);
+    s[24] = fma(p0, ry, s[24]); s[25] = fma(p1, ry, s[25]); s[26] = fma(p2, ry, s[26]);
+    const double g = fma(xi, rx, yi * ry);
+    s[27] = fma(-g, p0, s[27]); s[28] = fma(-g, p1, s[28]);
+    s[29] = fma(rx, rx, fma(ry, ry, s[29]));
     s[30] = fmax(s[30], fmax(fabs(rx), fabs(ry)));
 }
 // expand packed sums to the full symmetric 8x8 JtJ and Jtr

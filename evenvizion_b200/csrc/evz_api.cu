@@ -61,6 +61,7 @@ extern "C" int evz_set_option(evz_handle* h, int option, int value) {
         case EVZ_OPT_MATCH_VARIANT: h->opt_match_variant = value; return EVZ_OK;
         case EVZ_OPT_RANSAC_NO_PRUNE: h->opt_ransac_no_prune = value; return EVZ_OK;
         case EVZ_OPT_TIME_MATCH: h->opt_time_match = value; return EVZ_OK;
+        case EVZ_OPT_MATCH_DEBUG: h->opt_match_debug = value; return EVZ_OK;
         default: EVZ_SET_ERR(h, "evz_set_option: unknown option %d", option); return EVZ_E_ARG;
     }
 }

@@ -107,16 +107,26 @@ struct MatchArgs {
     int32_t* fix_count;        // number of rows left to match_fixup_kernel (reset by match_prepare_kernel)
     int32_t* fix_list;         // [fix_capacity] item * 256 + row
     int fix_capacity;
+    int dbg;                   // EVZ_OPT_MATCH_DEBUG: 1 = the V-space epilogue releases every accumulator without draining it
+    int pair_mode;             // 1: items are (pair, block of 512 query rows) shared by a CTA pair; work item index =
+                               //    2 * list index + CTA rank (match_top2_vkernel_t<2>)
 };
 
 __device__ __forceinline__ Item load_item(const MatchArgs& a, int it) {
     Item r;
-    const int p = a.items[2 * it], blk = a.items[2 * it + 1];
+    const int li = a.pair_mode ? it >> 1 : it;
+    const int p = a.items[2 * li];
+    int blk = a.items[2 * li + 1];
     const int qf = a.pair_q[p], tf = a.pair_t[p];
     const int nq = a.n_kp[qf];
+    int sub_left = nq - blk * kBlockQ;
+    if (a.pair_mode) {                              // both CTAs of a pair issue the same MMAs: the sub-tile count is
+        sub_left = nq - 2 * blk * kBlockQ;          // that of the first (fuller) block; the second block may be empty
+        blk = 2 * blk + (it & 1);
+    }
     r.q_row0 = a.row_off[qf] + blk * kBlockQ;
-    r.nq_left = nq - blk * kBlockQ;                 // valid query rows in this block (may exceed 256)
-    r.n_sub = r.nq_left > 128 ? 2 : 1;
+    r.nq_left = nq - blk * kBlockQ;                 // valid query rows in this block (may exceed 256, or be <= 0 for the peer block)
+    r.n_sub = sub_left > 128 ? 2 : 1;
     r.t_row0 = a.row_off[tf];
     r.nt = a.n_kp[tf];
     r.n_tiles = (r.nt + kBlockT - 1) / kBlockT;
@@ -509,11 +519,11 @@ match_top2_kernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-// items[i] = (pair, query block): one entry per 256-row block of every pair's query frame.
+// items[i] = (pair, query block): one entry per block of rows_per_item (256; 512 for CTA pairs) rows of every pair's query frame.
 // Single CTA; pairs are scanned in chunks of blockDim.x.
 __global__ void build_items_kernel(const int32_t* n_kp, const int32_t* pair_q, int n_pairs,
                                    int32_t* items, int32_t* n_items, int capacity,
-                                   const int32_t* pair_flag, int want) {
+                                   const int32_t* pair_flag, int want, int rows_per_item) {
     __shared__ int warp_sums[32];
     __shared__ int base_s;
     if (threadIdx.x == 0) base_s = 0;
@@ -523,7 +533,7 @@ __global__ void build_items_kernel(const int32_t* n_kp, const int32_t* pair_q, i
         const int p = p0 + threadIdx.x;
         // pair_flag selects the pairs of this list (V-space kernel: 0, legacy fallback: 1)
         const bool take = p < n_pairs && (pair_flag == nullptr || pair_flag[p] == want);
-        const int nb = take ? (n_kp[pair_q[p]] + kBlockQ - 1) / kBlockQ : 0;
+        const int nb = take ? (n_kp[pair_q[p]] + rows_per_item - 1) / rows_per_item : 0;
         int incl = nb;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffff, incl, d); if (lane >= d) incl += t; }
@@ -591,12 +601,19 @@ constexpr int kFlagged    = -2;                           // top2_idx[row][0] of
 constexpr int kVC   = 16;                // columns per chunk of the V-space epilogue (8 or 16)
 constexpr int kVCps = kBlockT / kVC;     // chunks per tile
 constexpr int kVClog = kVC == 8 ? 5 : 4; // log2(kVCps)
-struct VCfg {
+// kCtas = 1: one CTA per work item (256 query rows).  kCtas = 2: a CTA pair (cta_group::2) shares every train
+// tile -- each CTA stages half of it (128 rows + their 4 KB of the fifth K block) and drains its own 256 query rows.
+template <int kCtas>
+struct VCfgT {
     static constexpr int threads   = 384;
+    static constexpr int stages    = kCtas == 2 ? 5 : kStages;         // train-tile ring depth
+    static constexpr int tile_rows = kBlockT / kCtas;                  // train rows this CTA stages per tile
+    static constexpr int tile_bytes = tile_rows * kRowBytes;
+    static constexpr int ecode_bytes = tile_rows * 32;
     static constexpr int q_off     = 0;                                // 2 x 32 KB
-    static constexpr int t_off     = q_off + 2 * kQBytes;              // kStages x 32 KB
-    static constexpr int e_off     = t_off + kStages * kTileBytes;     // kStages x 8 KB
-    static constexpr int a_off     = e_off + kStages * kECodeBytes;    // 4 KB: query-side fifth K block
+    static constexpr int t_off     = q_off + 2 * kQBytes;              // stages x 32 (16) KB
+    static constexpr int e_off     = t_off + stages * tile_bytes;      // stages x 8 (4) KB
+    static constexpr int a_off     = e_off + stages * ecode_bytes;     // 4 KB: query-side fifth K block
     static constexpr int slot_off  = a_off + 128 * 32;                 // [slot 2][part 4][row 256] x 16 B
     static constexpr int part_stride = 256 * 16;
     static constexpr int slot_stride = (kVC / 4) * part_stride;
@@ -604,7 +621,7 @@ struct VCfg {
     static constexpr int pb_off    = slot_off + 2 * slot_stride;       // 2 x pb_bytes, alternating per item
     static constexpr int item_off  = pb_off + 2 * pb_bytes;
     static constexpr int bar_off   = item_off + 2 * static_cast<int>(sizeof(Item));
-    static constexpr int n_bars    = 2 * kStages + 2 + 2 + 2 + 2;
+    static constexpr int n_bars    = 2 * stages + 2 + 2 + 2 + 2 + (kCtas == 2 ? stages + 2 : 0);
     static constexpr int tmem_off  = bar_off + n_bars * 8;
     static constexpr int total     = tmem_off + 16;
     static constexpr int smem_bytes = total + 1024;
@@ -623,6 +640,7 @@ __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t smem_addr_bytes, uin
 }
 
 // one chunk of kVC raw accumulator values: chunk key, sorted top-3 update, predicated save
+template <int kPartStride>
 __device__ __forceinline__ void vchunk(const uint32_t* r, uint32_t tagc, uint32_t mul, uint32_t& M1, uint32_t& M2,
                                        uint32_t& M3, uint32_t& sec, uint32_t sum) {
     uint32_t cm;
@@ -640,6 +658,8 @@ __device__ __forceinline__ void vchunk(const uint32_t* r, uint32_t tagc, uint32_
     const uint32_t alt = sum - sec;
     uint32_t nsec;
     if (kVC == 16) {
+        // (a predicated-off STS.128 still costs its LSU issue slot: all-false predicates measured no faster, removing the
+        // four stores +28 %; skipping them with a warp-uniform vote + branch when no lane saves measured 13 % SLOWER)
         asm volatile("{\n\t.reg .pred p1, p2;\n\t"
                      "setp.gt.u32 p2, %2, %4;\n\t"
                      "setp.gt.u32 p1, %2, %3;\n\t"
@@ -651,7 +671,7 @@ __device__ __forceinline__ void vchunk(const uint32_t* r, uint32_t tagc, uint32_
                      : "=&r"(nsec) : "r"(sec), "r"(cmk), "r"(M1), "r"(M2), "r"(alt),
                        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                        "r"(r[8 % kVC]), "r"(r[9 % kVC]), "r"(r[10 % kVC]), "r"(r[11 % kVC]), "r"(r[12 % kVC]), "r"(r[13 % kVC]),
-                       "r"(r[14 % kVC]), "r"(r[15 % kVC]), "n"(VCfg::part_stride) : "memory");
+                       "r"(r[14 % kVC]), "r"(r[15 % kVC]), "n"(kPartStride) : "memory");
     } else {
         asm volatile("{\n\t.reg .pred p1, p2;\n\t"
                      "setp.gt.u32 p2, %2, %4;\n\t"
@@ -661,7 +681,7 @@ __device__ __forceinline__ void vchunk(const uint32_t* r, uint32_t tagc, uint32_
                      "selp.u32 %0, %5, %1, p1;\n\t}"
                      : "=&r"(nsec) : "r"(sec), "r"(cmk), "r"(M1), "r"(M2), "r"(alt),
                        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-                       "n"(VCfg::part_stride) : "memory");
+                       "n"(kPartStride) : "memory");
     }
     sec = nsec;
     const uint32_t t = min(M1, cmk), u = __vimin3_u32(M1, M2, cmk);
@@ -679,30 +699,38 @@ __device__ __forceinline__ void keep_alive16(const uint32_t* r) {
 
 // one accumulator row (256 columns): 8 batches of 32 columns, TMEM loads one batch ahead; the accumulator is
 // handed back to the MMA warp as soon as its last column is in registers
+template <int kCtas>
 __device__ __forceinline__ void drain_v(uint32_t taddr, uint32_t mul, uint32_t& M1, uint32_t& M2, uint32_t& M3,
-                                        uint32_t& sec, uint32_t sum, uint64_t* acc_empty, int lane) {
+                                        uint32_t& sec, uint32_t sum, uint32_t acc_empty, int lane) {
+    constexpr int kB = 8;
     uint32_t r[2][32];
     tmem_ld_32x32b_x32(taddr, r[0]);
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
+    for (int b = 0; b < kB; ++b) {
         tmem_ld_wait_dep(r[b & 1]);
-        if (b + 1 < 8) {
+        if (b + 1 < kB) {
             tmem_ld_32x32b_x32(taddr + (b + 1) * 32, r[(b + 1) & 1]);
         } else {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty);
+            if (lane == 0) {
+                if (kCtas == 2) mbar_arrive_cluster(acc_empty);      // the leader CTA's barrier collects both CTAs
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(acc_empty) : "memory");
+            }
         }
 #pragma unroll
-        for (int c = 0; c < 32 / kVC; ++c) vchunk(&r[b & 1][kVC * c], 254 - (32 / kVC) * b - c, mul, M1, M2, M3, sec, sum);
+        for (int c = 0; c < 32 / kVC; ++c)
+            vchunk<VCfgT<kCtas>::part_stride>(&r[b & 1][kVC * c], 254 - (32 / kVC) * b - c, mul, M1, M2, M3, sec, sum);
         keep_alive16(&r[b & 1][0]);
         keep_alive16(&r[b & 1][16]);
     }
 }
 
-__global__ void __launch_bounds__(VCfg::threads, 1)
-match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args) {
-    using Cfg = VCfg;
+template <int kCtas>
+__global__ void __launch_bounds__(VCfgT<kCtas>::threads, 1)
+match_top2_vkernel_t(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_half, const MatchArgs args) {
+    using Cfg = VCfgT<kCtas>;
+    constexpr int kSt = Cfg::stages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* q_s = smem + Cfg::q_off;
@@ -711,29 +739,38 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
     uint8_t* a_s = smem + Cfg::a_off;
     Item* item_s = reinterpret_cast<Item*>(smem + Cfg::item_off);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::bar_off);
-    uint64_t* full = bars;                       // [kStages] train tile + its fifth K block landed (TMA tx)
-    uint64_t* empty = full + kStages;            // [kStages] MMA commit
-    uint64_t* q_full = empty + kStages;          // [2] query block landed + item descriptor published
+    uint64_t* full = bars;                       // [kSt] this CTA's (part of the) train tile + its fifth K block landed (TMA tx)
+    uint64_t* empty = full + kSt;                // [kSt] MMA commit
+    uint64_t* q_full = empty + kSt;              // [2] query block landed + item descriptor published
     uint64_t* q_empty = q_full + 2;              // [2] MMA commit + 8 epilogue warps
     uint64_t* acc_full = q_empty + 2;            // [2] accumulator (= query sub-tile) ready (MMA commit)
-    uint64_t* acc_empty = acc_full + 2;          // [2] accumulator drained (4 epilogue warps each)
+    uint64_t* acc_empty = acc_full + 2;          // [2] accumulator drained (its 4 epilogue warps; CTA pair: of both CTAs, on the leader's barrier)
+    uint64_t* pfull = acc_empty + 2;             // [kSt] CTA pair, leader only: the peer's half of the train tile landed
+    uint64_t* pq_full = pfull + kSt;             // [2]   CTA pair, leader only: the peer's query block landed
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + Cfg::tmem_off);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = kCtas == 2 ? cluster_ctarank() : 0u;           // 0 = leader of the CTA pair (issues the MMAs)
+    const int unit = blockIdx.x / kCtas, n_units = gridDim.x / kCtas;   // CTA (pair) index: stride over the item list
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap);
-        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        if (kCtas == 2) tma_prefetch_desc(&tmap_half);
+        for (int i = 0; i < kSt; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1 + 8);
-            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4 * kCtas);
+        }
+        if (kCtas == 2) {
+            for (int i = 0; i < kSt; ++i) mbar_init(&pfull[i], 1);
+            for (int i = 0; i < 2; ++i) mbar_init(&pq_full[i], 1);
         }
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_ptr_s, 512);
-        tmem_relinquish();
+        if (kCtas == 2) { tmem_alloc_pair(tmem_ptr_s, 512); tmem_relinquish_pair(); }
+        else            { tmem_alloc(tmem_ptr_s, 512); tmem_relinquish(); }
     }
     if (warp == 3) {
         // query-side fifth K block: every row = (255 x 30, 1, 0), no-swizzle core-matrix layout
@@ -744,7 +781,8 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
         fence_proxy_async();
     }
     tc_fence_before();
-    __syncthreads();
+    if (kCtas == 2) cluster_sync_all();          // the peer's barriers must be initialised before anything arrives on them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_s;
     const int n_items = *args.n_items;
@@ -753,8 +791,8 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
         // ------------------------------------------------------------- TMA producer (polling waits, single thread)
         if (lane == 0) {
             uint32_t stage = 0, sphase = 0, qi = 0;
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-                const Item im = load_item(args, it);
+            for (int it = unit; it < n_items; it += n_units) {
+                const Item im = load_item(args, it * kCtas + rank);
                 const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
                 ++qi;
                 mbar_wait_spin(&q_empty[qb], qph ^ 1);
@@ -764,58 +802,83 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
                 tma_load_2d(q_s + qb * kQBytes, &tmap, 0, im.q_row0, &q_full[qb]);
                 bulk_load_1d(smem + Cfg::pb_off + qb * Cfg::pb_bytes, args.pbits + static_cast<size_t>(im.t_row0 >> 8) * 8,
                              im.n_tiles * 32, &q_full[qb]);
-                const uint8_t* ecode = args.ecode + static_cast<size_t>(im.t_row0 >> 8) * kECodeBytes;
+                // this CTA's part of every train tile: all 256 rows, or rows [128 rank, 128 rank + 128) of a CTA pair
+                const CUtensorMap* tm_t = kCtas == 2 ? &tmap_half : &tmap;
+                const int t_row = im.t_row0 + static_cast<int>(rank) * Cfg::tile_rows;
+                const uint8_t* ecode = args.ecode + static_cast<size_t>(im.t_row0 >> 8) * kECodeBytes + rank * Cfg::ecode_bytes;
                 for (int n = 0; n < im.n_tiles; ++n) {
-                    // the ring is only kStages deep: pull the tile that will be loaded kStages iterations from now
+                    // the ring is only a few tiles deep: pull the tile that will be loaded kSt iterations from now
                     // into L2 already, so that its TMA load is an L2 hit
-                    if (n + kStages < im.n_tiles) {
-                        tma_prefetch_2d(&tmap, 0, im.t_row0 + (n + kStages) * kBlockT);
-                        bulk_prefetch_1d(ecode + static_cast<size_t>(n + kStages) * kECodeBytes, kECodeBytes);
+                    if (n + kSt < im.n_tiles) {
+                        tma_prefetch_2d(tm_t, 0, t_row + (n + kSt) * kBlockT);
+                        bulk_prefetch_1d(ecode + static_cast<size_t>(n + kSt) * kECodeBytes, Cfg::ecode_bytes);
                     }
                     mbar_wait_spin(&empty[stage], sphase ^ 1);
-                    mbar_arrive_expect_tx(&full[stage], kTileBytes + kECodeBytes);
-                    tma_load_2d(t_s + stage * kTileBytes, &tmap, 0, im.t_row0 + n * kBlockT, &full[stage]);
-                    bulk_load_1d(e_s + stage * kECodeBytes, ecode + static_cast<size_t>(n) * kECodeBytes, kECodeBytes, &full[stage]);
-                    if (++stage == kStages) { stage = 0; sphase ^= 1; }
+                    mbar_arrive_expect_tx(&full[stage], Cfg::tile_bytes + Cfg::ecode_bytes);
+                    tma_load_2d(t_s + stage * Cfg::tile_bytes, tm_t, 0, t_row + n * kBlockT, &full[stage]);
+                    bulk_load_1d(e_s + stage * Cfg::ecode_bytes, ecode + static_cast<size_t>(n) * kECodeBytes, Cfg::ecode_bytes, &full[stage]);
+                    if (++stage == kSt) { stage = 0; sphase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {
             // accumulator = query sub-tile.  The waits of this single thread poll: a tcgen05.mma issue blocks
             // until the tensor pipe accepts it, so the pipe only stays fed while this thread is never late,
-            // and a suspended try_wait wakes up late.
-            constexpr uint32_t idesc = umma_idesc_u8(128, kBlockT);
+            // and a suspended try_wait wakes up late.  CTA pair: this thread issues the 256-row MMAs of both
+            // CTAs (rows 0-127 = its own query sub-tile, 128-255 = the peer's; each CTA supplies 128 of the 256
+            // train rows) and its commits arrive on the barriers of both CTAs.
+            constexpr uint32_t idesc = umma_idesc_u8(128 * kCtas, kBlockT);
             const uint64_t da_e = umma_desc_nosw(smem_u32(a_s), 128, 256);
             uint32_t stage = 0, sphase = 0, qi = 0, gs[2] = {0, 0};
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            for (int it = unit; it < n_items; it += n_units) {
                 const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
                 ++qi;
                 mbar_wait_spin(&q_full[qb], qph);
+                if (kCtas == 2) mbar_wait_spin_cluster(&pq_full[qb], qph);
                 const int n_tiles = item_s[qb].n_tiles, n_sub = item_s[qb].n_sub;
                 const uint32_t q_addr = smem_u32(q_s + qb * kQBytes);
                 for (int n = 0; n < n_tiles; ++n) {
                     mbar_wait_spin(&full[stage], sphase);
-                    const uint32_t t_addr = smem_u32(t_s + stage * kTileBytes);
-                    const uint64_t db_e = umma_desc_nosw(smem_u32(e_s + stage * kECodeBytes), 128, 256);
+                    if (kCtas == 2) mbar_wait_spin_cluster(&pfull[stage], sphase);
+                    const uint32_t t_addr = smem_u32(t_s + stage * Cfg::tile_bytes);
+                    const uint64_t db_e = umma_desc_nosw(smem_u32(e_s + stage * Cfg::ecode_bytes), 128, 256);
                     for (int sub = 0; sub < n_sub; ++sub) {
                         const uint32_t aph = gs[sub]++ & 1;
-                        mbar_wait_spin(&acc_empty[sub], aph ^ 1);
+                        if (kCtas == 2) mbar_wait_spin_cluster(&acc_empty[sub], aph ^ 1);
+                        else mbar_wait_spin(&acc_empty[sub], aph ^ 1);
                         tc_fence_after();
 #pragma unroll
                         for (int k = 0; k < kRowBytes / 32; ++k) {
                             const uint64_t da = umma_desc_sw128(q_addr + sub * (128 * kRowBytes) + k * 32);
                             const uint64_t db = umma_desc_sw128(t_addr + k * 32);
-                            umma_i8(tmem_base + sub * kBlockT, da, db, idesc, k > 0 ? 1u : 0u);
+                            if (kCtas == 2) umma_i8_pair(tmem_base + sub * kBlockT, da, db, idesc, k > 0 ? 1u : 0u);
+                            else umma_i8(tmem_base + sub * kBlockT, da, db, idesc, k > 0 ? 1u : 0u);
                         }
-                        umma_i8(tmem_base + sub * kBlockT, da_e, db_e, idesc, 1u);
-                        umma_commit(&acc_full[sub]);
+                        if (kCtas == 2) { umma_i8_pair(tmem_base + sub * kBlockT, da_e, db_e, idesc, 1u); umma_commit_pair(&acc_full[sub]); }
+                        else            { umma_i8(tmem_base + sub * kBlockT, da_e, db_e, idesc, 1u); umma_commit(&acc_full[sub]); }
                     }
-                    umma_commit(&empty[stage]);
-                    if (++stage == kStages) { stage = 0; sphase ^= 1; }
+                    if (kCtas == 2) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);
+                    if (++stage == kSt) { stage = 0; sphase ^= 1; }
                 }
-                umma_commit(&q_empty[qb]);
+                if (kCtas == 2) umma_commit_pair(&q_empty[qb]); else umma_commit(&q_empty[qb]);
+            }
+        } else if (kCtas == 2 && lane == 0) {
+            // peer CTA of a pair: forward "my query block / my half of the tile has landed" to the leader's barriers
+            const uint32_t r_pfull = mapa_u32(smem_u32(pfull), 0), r_pq_full = mapa_u32(smem_u32(pq_full), 0);
+            uint32_t stage = 0, sphase = 0, qi = 0;
+            for (int it = unit; it < n_items; it += n_units) {
+                const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+                ++qi;
+                mbar_wait_spin(&q_full[qb], qph);
+                const int n_tiles = item_s[qb].n_tiles;     // read before the leader can release the item
+                mbar_arrive_cluster(r_pq_full + qb * 8);
+                for (int n = 0; n < n_tiles; ++n) {
+                    mbar_wait_spin(&full[stage], sphase);
+                    mbar_arrive_cluster(r_pfull + stage * 8);
+                    if (++stage == kSt) { stage = 0; sphase ^= 1; }
+                }
             }
         }
     } else if (warp >= 4) {
@@ -826,14 +889,15 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
         const uint32_t slot_a = smem_u32(smem + Cfg::slot_off) + row * 16, slot_b = slot_a + Cfg::slot_stride;
         const uint32_t sum = slot_a + slot_b;
         const uint32_t taddr = tmem_base + grp * kBlockT + (static_cast<uint32_t>(quarter * 32) << 16);
+        const uint32_t acc_empty_a = kCtas == 2 ? mapa_u32(smem_u32(&acc_empty[grp]), 0) : smem_u32(&acc_empty[grp]);
         uint32_t g = 0, qi = 0;
-        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        for (int it = unit; it < n_items; it += n_units) {
             const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
             ++qi;
             mbar_wait(&q_full[qb], qph);
             const Item im = item_s[qb];
             if (grp < im.n_sub) {
-                const int qkey = __ldg(args.ckey + im.q_row0 + row);
+                const int qkey = row < im.nq_left ? __ldg(args.ckey + im.q_row0 + row) : 0;
                 // sorted top-3 of chunk keys, the slot that holds the second-best chunk, and the position
                 // (tile * 16 + chunk) of the chunks in the best / second-best slot
                 uint32_t M1 = 0, M2 = 0, M3 = 0, sec = slot_b;
@@ -844,7 +908,17 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
                     const uint32_t o1 = M1, o2 = M2;
                     mbar_wait(&acc_full[grp], g & 1);
                     tc_fence_after();
-                    drain_v(taddr, args.mul256, M1, M2, M3, sec, sum, &acc_empty[grp], lane);
+                    if (args.dbg == 1) {                 // measurement of the TMA / MMA front end alone: results are garbage
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (kCtas == 2) mbar_arrive_cluster(acc_empty_a);
+                            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(acc_empty_a) : "memory");
+                        }
+                        ++g;
+                        continue;
+                    }
+                    drain_v<kCtas>(taddr, args.mul256, M1, M2, M3, sec, sum, acc_empty_a, lane);
                     ++g;
                     const int nTb = M1 == o1 ? Tb : n * kVCps + 254 - static_cast<int>(M1 & 255u);
                     Ts = (M1 != o1 && M2 == o1) ? Tb : (M2 == o2 ? Ts : n * kVCps + 254 - static_cast<int>(M2 & 255u));
@@ -904,18 +978,24 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
                     reinterpret_cast<int2*>(args.top2_d2)[o_row] = od;
                     if (flagged) {
                         const int pos = atomicAdd(args.fix_count, 1);
-                        if (pos < args.fix_capacity) args.fix_list[pos] = it * 256 + row;
+                        if (pos < args.fix_capacity) args.fix_list[pos] = (it * kCtas + static_cast<int>(rank)) * 256 + row;
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&q_empty[qb]);
         }
-    }
+        }
 
     tc_fence_before();
-    __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (kCtas == 2) {
+        // neither CTA may leave (or free its TMEM) while the peer can still touch its shared memory or barriers
+        cluster_sync_all();
+        if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+    } else {
+        __syncthreads();
+        if (warp == 2) tmem_dealloc(tmem_base, 512);
+    }
 }
 
 // Per pair: hmax / range test of the train frame, then the 32 code bytes of every train row in the
@@ -1049,6 +1129,15 @@ static int ensure_tmap(evz_handle* h, const uint8_t* desc, int64_t total_rows) {
         EVZ_SET_ERR(h, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld)", static_cast<int>(r), static_cast<long long>(total_rows));
         return EVZ_E_CUDA;
     }
+    // CTA-pair kernel: each CTA of a pair stages 128 of the 256 rows of a train tile
+    const cuuint32_t box_half[2] = {static_cast<cuuint32_t>(evz::kRowBytes), 128u};
+    const CUresult r2 = h->encode(&h->tmap_half, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(desc), dims, strides, box_half, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r2 != CUDA_SUCCESS) {
+        EVZ_SET_ERR(h, "cuTensorMapEncodeTiled (half tiles) failed with CUresult %d (rows=%lld)", static_cast<int>(r2), static_cast<long long>(total_rows));
+        return EVZ_E_CUDA;
+    }
     h->tmap_ptr = desc;
     h->tmap_rows = total_rows;
     return EVZ_OK;
@@ -1072,7 +1161,8 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
     // EVZ_OPT_MATCH_VARIANT: 0 = V-space kernel (norm in a fifth K block; default); legacy kernel: 1 = exact
     // per-element top-2, 2 = chunk minima of 16, 5 (and any other value) = chunk minima of 8
     const int variant = h->opt_match_variant;
-    const bool vspace = variant == 0;
+    const bool vpair = variant == 7;                 // V-space kernel on CTA pairs (cta_group::2)
+    const bool vspace = variant == 0 || vpair;
     // scratch: [counters 256 B][items A][items B][pair_hmax][pair_flag][ecode]
     const size_t items_bytes = evz_align_up(capacity * 8, 256), pair_bytes = evz_align_up(static_cast<size_t>(n_pairs) * 4, 256);
     const size_t fix_bytes = evz_align_up(capacity * 256 * 4, 256);          // every row of every item, at worst
@@ -1086,7 +1176,7 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
     int32_t* n_items = reinterpret_cast<int32_t*>(sb);
     int32_t* items = reinterpret_cast<int32_t*>(sb + 256);
     evz::MatchArgs a{ckey, row_off, n_kp, pair_q, pair_t, out_off, items, n_items, top2_idx, top2_d2, -512, nullptr, nullptr, nullptr, 256u,
-                     nullptr, nullptr, 0};
+                     nullptr, nullptr, 0, h->opt_match_debug, 0};
 #define EVZ_MATCH_LAUNCH(CH, EW)                                                                                         \
     do {                                                                                                                 \
         using Cfg = evz::MatchCfg<CH, EW>;                                                                               \
@@ -1111,14 +1201,17 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
         a.pbits = pbits;
         evz::match_prepare_kernel<<<n_pairs, 256, 0, st>>>(ckey, row_off, n_kp, pair_t, pair_hmax, pair_flag, ecode, pbits, a.fix_count);
         EVZ_LAUNCH_CHECK(h);
-        evz::build_items_kernel<<<1, 1024, 0, st>>>(n_kp, pair_q, n_pairs, items, n_items, static_cast<int>(capacity), pair_flag, 0);
-        evz::build_items_kernel<<<1, 1024, 0, st>>>(n_kp, pair_q, n_pairs, items_slow, n_items_slow, static_cast<int>(capacity), pair_flag, 1);
+        evz::build_items_kernel<<<1, 1024, 0, st>>>(n_kp, pair_q, n_pairs, items, n_items, static_cast<int>(capacity), pair_flag, 0,
+                                                    vpair ? 2 * evz::kBlockQ : evz::kBlockQ);
+        evz::build_items_kernel<<<1, 1024, 0, st>>>(n_kp, pair_q, n_pairs, items_slow, n_items_slow, static_cast<int>(capacity), pair_flag, 1,
+                                                    evz::kBlockQ);
         EVZ_LAUNCH_CHECK(h);
         a.pair_hmax = pair_hmax;
         a.ecode = ecode;
         static bool v_attr_set = false;
         if (!v_attr_set) {
-            EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
+            EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfgT<1>::smem_bytes));
+            EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfgT<2>::smem_bytes));
             v_attr_set = true;
         }
         cudaEvent_t* tev = nullptr;
@@ -1130,7 +1223,22 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
             tev = h->match_ev[h->match_calls++ & 15];
             EVZ_CUDA_CHECK(h, cudaEventRecord(tev[0], st));
         }
-        evz::match_top2_vkernel<<<h->sm_count, evz::VCfg::threads, evz::VCfg::smem_bytes, st>>>(h->tmap, a);
+        if (vpair) {
+            a.pair_mode = 1;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(static_cast<unsigned>(h->sm_count / 2 * 2));
+            cfg.blockDim = dim3(evz::VCfgT<2>::threads);
+            cfg.dynamicSmemBytes = evz::VCfgT<2>::smem_bytes;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            EVZ_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, evz::match_top2_vkernel_t<2>, h->tmap, h->tmap_half, a));
+        } else {
+            evz::match_top2_vkernel_t<1><<<h->sm_count, evz::VCfgT<1>::threads, evz::VCfgT<1>::smem_bytes, st>>>(h->tmap, h->tmap_half, a);
+        }
         EVZ_LAUNCH_CHECK(h);
         if (tev) EVZ_CUDA_CHECK(h, cudaEventRecord(tev[1], st));
         evz::match_fixup_kernel<<<h->sm_count * 8, 128, 0, st>>>(desc, a);
@@ -1139,9 +1247,10 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
         a.items = items_slow;
         a.n_items = n_items_slow;
         a.pair_hmax = nullptr;
+        a.pair_mode = 0;
         EVZ_MATCH_LAUNCH(8, 8);
     } else {
-        evz::build_items_kernel<<<1, 1024, 0, st>>>(n_kp, pair_q, n_pairs, items, n_items, static_cast<int>(capacity), nullptr, 0);
+        evz::build_items_kernel<<<1, 1024, 0, st>>>(n_kp, pair_q, n_pairs, items, n_items, static_cast<int>(capacity), nullptr, 0, evz::kBlockQ);
         EVZ_LAUNCH_CHECK(h);
         switch (variant) {
             case 1:  EVZ_MATCH_LAUNCH(0, 8); break;

@@ -82,11 +82,16 @@ int         evz_sm_count(const evz_handle* h);
 #define EVZ_OPT_MATCH_VARIANT  2  /* match kernel: 0 default ("V-space": the train norm enters the accumulator through a
                                      fifth K block, max-tree epilogue, exact resolution from two saved chunks + fix-up);
                                      key-space kernel (distance/index keys formed per element): 5 chunk-8 minima + saved
-                                     best chunk, 1 exact top-2 per element, 2 chunk-16 minima */
+                                     best chunk, 1 exact top-2 per element, 2 chunk-16 minima;
+                                     7: the V-space kernel on CTA pairs (tcgen05 cta_group::2: a 2-CTA cluster shares every
+                                     train tile, each CTA stages half of it and drains its own 256 query rows) -- bit-identical,
+                                     measured slower than 0 on B200, kept for A/B */
 #define EVZ_OPT_RANSAC_NO_PRUNE 3  /* 1: score every valid hypothesis even after one of them counted all matches as inliers
                                      (default 0: hypotheses that can no longer win the (count desc, index asc) arg-max are skipped) */
 #define EVZ_OPT_TIME_MATCH     4  /* 1: evz_match_top2 brackets its main kernel with CUDA events on the caller's stream (a ring of
                                      16 pairs, one per call); read them with evz_match_kernel_ms after synchronising */
+#define EVZ_OPT_MATCH_DEBUG    5  /* measurement only, NOT result-preserving: 1 = the V-space epilogue releases every accumulator
+                                     without draining it (times the TMA / tcgen05 front end alone; outputs are undefined) */
 int         evz_set_option(evz_handle* h, int option, int value);
 /* elapsed time of the main match kernel of the k-th most recent evz_match_top2 call (k = 0: the last one), for the
  * roofline line of bench.py.  The stream must have been synchronised; returns EVZ_E_ARG when no such record exists. */

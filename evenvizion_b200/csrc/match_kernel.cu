@@ -697,20 +697,25 @@ __device__ __forceinline__ void keep_alive16(const uint32_t* r) {
                        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
 }
 
-// one accumulator row (256 columns): 8 batches of 32 columns, TMEM loads one batch ahead; the accumulator is
-// handed back to the MMA warp as soon as its last column is in registers
+// one accumulator row (256 columns) in 16 loads of one chunk (16 columns) each, two loads ahead of the chunk being
+// processed, into four 16-register buffers: the load for chunk c + 2 overwrites the registers of chunk c - 2, whose
+// (predicated) stores were issued a whole chunk ago.  With 32-column loads one batch ahead, every load had to wait
+// for the stores of the batch just processed to read their operands (write-after-read on the registers, paid
+// whether or not the predicate is true).  The accumulator is handed back to the MMA warp as soon as its last
+// column is in registers.
 template <int kCtas>
 __device__ __forceinline__ void drain_v(uint32_t taddr, uint32_t mul, uint32_t& M1, uint32_t& M2, uint32_t& M3,
                                         uint32_t& sec, uint32_t sum, uint32_t acc_empty, int lane) {
-    constexpr int kB = 8;
-    uint32_t r[2][32];
-    tmem_ld_32x32b_x32(taddr, r[0]);
+    static_assert(kVC == 16, "one TMEM load per chunk");
+    uint32_t r[4][16];
+    tmem_ld_32x32b_x16(taddr, r[0]);
+    tmem_ld_32x32b_x16(taddr + 16, r[1]);
 #pragma unroll
-    for (int b = 0; b < kB; ++b) {
-        tmem_ld_wait_dep(r[b & 1]);
-        if (b + 1 < kB) {
-            tmem_ld_32x32b_x32(taddr + (b + 1) * 32, r[(b + 1) & 1]);
-        } else {
+    for (int c = 0; c < kVCps; ++c) {
+        tmem_ld_wait_dep(r[c & 3]);
+        if (c + 2 < kVCps) {
+            tmem_ld_32x32b_x16(taddr + (c + 2) * 16, r[(c + 2) & 3]);
+        } else if (c + 2 == kVCps) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -718,11 +723,8 @@ __device__ __forceinline__ void drain_v(uint32_t taddr, uint32_t mul, uint32_t& 
                 else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(acc_empty) : "memory");
             }
         }
-#pragma unroll
-        for (int c = 0; c < 32 / kVC; ++c)
-            vchunk<VCfgT<kCtas>::part_stride>(&r[b & 1][kVC * c], 254 - (32 / kVC) * b - c, mul, M1, M2, M3, sec, sum);
-        keep_alive16(&r[b & 1][0]);
-        keep_alive16(&r[b & 1][16]);
+        vchunk<VCfgT<kCtas>::part_stride>(&r[c & 3][0], 254 - c, mul, M1, M2, M3, sec, sum);
+        keep_alive16(&r[c & 3][0]);
     }
 }
 

@@ -583,17 +583,24 @@ __global__ void build_items_kernel(const int32_t* n_kp, const int32_t* pair_q, i
 // and third chunk: ~1e-3 of the rows on descriptor-like data, every row on degenerate data) are flagged
 // and recomputed by match_fixup_kernel (dp4a brute force, one CTA per row).
 //
-// Measured (B200, 2048 keypoints/frame, profiles/r01e_*): 1.8 warp instructions per 32 outputs against 3.3
+// Measured (B200, 2048 keypoints/frame, profiles/r01e_*, r01f): 1.8 warp instructions per 32 outputs against 3.3
 // in the key-space kernel; tensor pipe active 56 % (45 % algorithmic + the fifth K block), issue slots 45 %,
-// ALU pipe 57 %.  What bounds it now is the SHARED-MEMORY DATA PIPE (one 128-byte wavefront per clock): the
-// tensor core's operand fetch takes 41 % of it (10 MMAs x 12 KB per tile: the 128-row A sub-tile is re-read
-// for every MMA), the predicated chunk saves 36 % (1.5 wavefronts per STS.128: the few active lanes are
-// spread over the four quarter-warp phases), other LSU traffic 10 %, and the TMA writes of the incoming
-// tiles come on top -- about 2 170 wavefronts per tile against a measured tile time of 2 100-2 300 clk.
-// That is why variants that only cut instructions (chunks of 32), only shorten the accumulator hand-off (all
-// eight warps per accumulator, 16 epilogue warps), poll barriers from all threads or use N = 128 MMAs (more
-// operand fetch per MAC) measured equal or slower; chunks of 8 (kVC) halve the saved bytes but add
-// instructions: faster at 1024 keypoints, slower at 8192.  See DESIGN.md.
+// ALU pipe 57 %.  The TMA / tcgen05 front end alone (EVZ_OPT_MATCH_DEBUG = 1: accumulators released undrained)
+// runs at 2.75 POP/s (2048 keypoints) to 3.2 POP/s (8192), the rate of the cuBLASLt int8 GEMM; the kernel runs at
+// 1.9-2.0 / 2.3, so the epilogue is the bound.  What the r01f experiments showed about it (all bit-exact):
+//   * the four predicated STS.128 of a chunk cost 22 % of the kernel whether or not any lane stores (all-false
+//     predicates: no change; stores compiled out: 1.14 -> 0.89 ms per 2 000 pairs), but skipping them with a
+//     warp-uniform vote + branch when no lane saves is 11-13 % SLOWER (per chunk, or after both chunks of a
+//     batch), also at 8192 keypoints where 60 % of the chunks have no saving lane;
+//   * it is not the shared-memory data pipe (the r01e reading): CTA pairs (cta_group::2, variant 7: half the TMA
+//     writes, a third less operand fetch per SM) run at parity, not faster;
+//   * it is not the accumulator hand-off either: eight warps per accumulator (column halves, merged at the end
+//     of the item; possible with the smaller rings of the pair layout) are 25 % slower with 8 epilogue warps (all
+//     of them wait for the same accumulator) and 9 % slower with 16;
+//   * 32-column loads one batch ahead and 16-column loads two chunks ahead (now; 144 -> 112 registers) are equal.
+// Chunks of 32 columns, N = 128 MMAs and polling barriers from all threads measured equal or slower in r01e;
+// chunks of 8 (kVC) halve the saved bytes but add instructions: faster at 1024 keypoints, slower at 8192.
+// See DESIGN.md.
 constexpr int kECodeBytes = kBlockT * 32;                 // fifth K block of one train tile
 constexpr int kEMax       = 255 * (30 * 255) + 254;       // largest representable E_c
 constexpr int kFlagged    = -2;                           // top2_idx[row][0] of a row left to the fix-up kernel

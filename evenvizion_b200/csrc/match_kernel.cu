@@ -670,11 +670,11 @@ __device__ __forceinline__ void vchunk(const uint32_t* r, uint32_t tagc, uint32_
         asm volatile("{\n\t.reg .pred p1, p2;\n\t"
                      "setp.gt.u32 p2, %2, %4;\n\t"
                      "setp.gt.u32 p1, %2, %3;\n\t"
+                     "selp.u32 %0, %5, %1, p1;\n\t"
                      "@p2 st.shared.v4.b32 [%1], {%6, %7, %8, %9};\n\t"
                      "@p2 st.shared.v4.b32 [%1+%22], {%10, %11, %12, %13};\n\t"
                      "@p2 st.shared.v4.b32 [%1+2*%22], {%14, %15, %16, %17};\n\t"
-                     "@p2 st.shared.v4.b32 [%1+3*%22], {%18, %19, %20, %21};\n\t"
-                     "selp.u32 %0, %5, %1, p1;\n\t}"
+                     "@p2 st.shared.v4.b32 [%1+3*%22], {%18, %19, %20, %21};\n\t}"
                      : "=&r"(nsec) : "r"(sec), "r"(cmk), "r"(M1), "r"(M2), "r"(alt),
                        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                        "r"(r[8 % kVC]), "r"(r[9 % kVC]), "r"(r[10 % kVC]), "r"(r[11 % kVC]), "r"(r[12 % kVC]), "r"(r[13 % kVC]),
@@ -918,6 +918,25 @@ match_top2_vkernel_t(const __grid_constant__ CUtensorMap tmap, const __grid_cons
                     mbar_wait(&acc_full[grp], g & 1);
                     tc_fence_after();
                     if (args.dbg == 1) {                 // measurement of the TMA / MMA front end alone: results are garbage
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (kCtas == 2) mbar_arrive_cluster(acc_empty_a);
+                            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(acc_empty_a) : "memory");
+                        }
+                        ++g;
+                        continue;
+                    }
+                    if (args.dbg == 2) {                 // measurement: TMEM loads only (no max tree, no saves); results are garbage
+                        uint32_t r[4][16];
+                        tmem_ld_32x32b_x16(taddr, r[0]);
+                        tmem_ld_32x32b_x16(taddr + 16, r[1]);
+#pragma unroll
+                        for (int c = 0; c < kVCps; ++c) {
+                            tmem_ld_wait_dep(r[c & 3]);
+                            if (c + 2 < kVCps) tmem_ld_32x32b_x16(taddr + (c + 2) * 16, r[(c + 2) & 3]);
+                            keep_alive16(&r[c & 3][0]);
+                        }
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {

@@ -590,7 +590,7 @@ __global__ void build_items_kernel(const int32_t* n_kp, const int32_t* pair_q, i
 // 1.9-2.0 / 2.3, so the epilogue is the bound.  What the r01f experiments showed about it (all bit-exact):
 //   * the four predicated STS.128 of a chunk cost 22 % of the kernel whether or not any lane stores (all-false
 //     predicates: no change; stores compiled out: 1.14 -> 0.89 ms per 2 000 pairs), but skipping them with a
-//     warp-uniform vote + branch when no lane saves is 11-13 % SLOWER (per chunk, or after both chunks of a
+//     warp-uniform vote + branch when no lane saves is 18 % SLOWER in a same-run A/B (per chunk, or after both chunks of a
 //     batch), also at 8192 keypoints where 60 % of the chunks have no saving lane;
 //   * it is not the shared-memory data pipe (the r01e reading): CTA pairs (cta_group::2, variant 7: half the TMA
 //     writes, a third less operand fetch per SM) run at parity, not faster;
@@ -666,7 +666,7 @@ __device__ __forceinline__ void vchunk(const uint32_t* r, uint32_t tagc, uint32_
     uint32_t nsec;
     if (kVC == 16) {
         // (a predicated-off STS.128 still costs its LSU issue slot: all-false predicates measured no faster, removing the
-        // four stores +28 %; skipping them with a warp-uniform vote + branch when no lane saves measured 13 % SLOWER)
+        // four stores +28 %; skipping them with a warp-uniform vote + branch when no lane saves measured 18 % SLOWER)
         asm volatile("{\n\t.reg .pred p1, p2;\n\t"
                      "setp.gt.u32 p2, %2, %4;\n\t"
                      "setp.gt.u32 p1, %2, %3;\n\t"

@@ -327,6 +327,7 @@ __device__ __forceinline__ void fused_thresholds(const float (&h)[8], float cmax
 // partial counts, final bounds.  (Two-phase scoring, see ransac_score_kernel.)
 struct PtRange { int i0, i1, mode; };
 constexpr int kFull = 0, kPrefix = 1, kSuffix = 2;
+constexpr int kLead = 32;                    // hypotheses of the fully scored leading batch of the two-phase scoring
 
 template <int NJ, bool kCheckDen>
 __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, const uint16_t* vlist,
@@ -648,8 +649,11 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     // (SUFFIX).  With 80 % inliers this retires every outlier-contaminated hypothesis after ~25 % of its work.
     // (At level >= 2 the first row goes alone instead: the rows after it are usually pruned by the cut it finds.)
     // One call site of score_slots in a small state machine keeps the kernel's code size down.
-    const int s1 = start + kRsThreads;
-    const bool two_phase = prune && a.level == 1 && n_valid > s1;
+    // (the batch that is scored against every match is only kLead hypotheses: sliced over the matches like a partial
+    // row it costs a quarter of a full row, and one all-inlier sample among 64 is as good as one among 256 for lb)
+    const bool lead = prune && a.level == 1;
+    const int s1 = start + (lead ? kLead : kRsThreads);
+    const bool two_phase = lead && n_valid > s1;
     int lb = 0;
     int sb = start, se = two_phase ? s1 : n_valid;
     PtRange rg{0, m, kFull};

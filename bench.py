@@ -152,6 +152,30 @@ def run_reference(args, cfg):
     }))
 
 
+def flann_agreement(desc_h, gpu_idx, gpu_surv, ratio=0.5):
+    """Reported only (north_star: "agreement with its FLANN path is reported as a rate"): the reference itself uses the
+    exact "BruteForce" matcher (matching.py:102-103), so the comparison is against stock cv2.FlannBasedMatcher
+    (KD-tree, trees=5, checks=50) followed by the same ratio test, on the first pairs of the benchmark chain.
+    top1 = share of query keypoints whose nearest neighbour agrees with the (exact) GPU result;
+    survivors_jaccard = |F and G| / |F or G| of the ratio-test survivor sets."""
+    try:
+        import cv2
+        fl = cv2.FlannBasedMatcher(dict(algorithm=1, trees=5), dict(checks=50))
+        same = tot = inter = union = 0
+        for k, (gi, gs) in enumerate(zip(gpu_idx, gpu_surv)):
+            q = desc_h[k + 1].numpy().astype(np.float32)
+            t = desc_h[k].numpy().astype(np.float32)
+            raw = fl.knnMatch(q, t, 2)
+            fi = np.array([m[0].trainIdx if len(m) else -1 for m in raw])
+            fs = np.array([len(m) == 2 and m[0].distance < m[1].distance * ratio for m in raw])
+            same += int((fi == gi[:len(fi)]).sum()); tot += len(fi)
+            inter += int((fs & gs[:len(fs)]).sum()); union += int((fs | gs[:len(fs)]).sum())
+        return {"top1": same / max(tot, 1), "survivors_jaccard": inter / max(union, 1), "pairs": len(gpu_idx),
+                "flann": "cv2.FlannBasedMatcher KD-tree trees=5 checks=50"}
+    except Exception as exc:                    # reported-only extra: never fail the benchmark line
+        return {"unavailable": repr(exc)[:200]}
+
+
 def int8_ceiling(torch, dev):
     """On-box dense int8 GEMM ceiling (cuBLASLt through torch._int_mm, 8192^3), TOP/s."""
     try:
@@ -276,6 +300,11 @@ def run_ours(args, cfg):
     kern_ms = [eng.match_kernel_ms(k) for k in range(min(args.steps, 16))]
     n_ok = int((r.status == 0).sum().item())
     mean_matches = float(r.m_cnt.float().mean().item())
+    # first pairs of the last step, kept for the reported-only FLANN agreement rate (rank 0, below)
+    flann_pairs = min(8, P)
+    flann_rows = [(int(st.row_off_h[q]), int(st.n_kp_h[q])) for q in range(1, flann_pairs + 1)]
+    flann_idx = [r.top2_idx[o:o + n, 0].cpu().numpy() for o, n in flann_rows]
+    flann_surv = [r.surv[o:o + n].cpu().numpy().astype(bool) for o, n in flann_rows]
     del r
 
     # ---- end to end through the public host API (pinned host buffers in, host arrays out)
@@ -320,6 +349,9 @@ def run_ours(args, cfg):
             cpu = {"value": n / sec, "unit": "pairs/s", "cores": cores, "kind": "port",
                    "sample": f"first {n} pairs of the same chain, one pass ({sec:.1f} s), {cores} single-threaded OpenCV workers, "
                              f"reference path restated in oracle/cpu_reference.py ({ok} pairs with a valid H)"}
+        flann = None
+        if world == 1 and not args.no_cpu:
+            flann = flann_agreement(desc_h, flann_idx, flann_surv)
         print(json.dumps({
             "metric": "frame-pairs/sec (match+RANSAC H)", "value": world * P / (ms_per_step * 1e-3), "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -344,6 +376,7 @@ def run_ours(args, cfg):
                          "note": "ops = 2*Nq*Nt*128 per pair (int8 MAC = 2 ops); the fifth K block that carries the train "
                                  "norms (+25 % tensor work) is not counted"},
             "cpu_baseline": cpu,
+            "flann_agreement": flann,
             "e2e": {"value": world * P / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
             "gpu_launches": ((KERNELS_PER_STEP_MULTI if world > 1 else KERNELS_PER_STEP) + (1 if K else 0)) * args.steps,

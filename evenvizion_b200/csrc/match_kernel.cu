@@ -597,7 +597,11 @@ __global__ void build_items_kernel(const int32_t* n_kp, const int32_t* pair_q, i
 //   * it is not the accumulator hand-off either: eight warps per accumulator (column halves, merged at the end
 //     of the item; possible with the smaller rings of the pair layout) are 25 % slower with 8 epilogue warps (all
 //     of them wait for the same accumulator) and 9 % slower with 16;
-//   * 32-column loads one batch ahead and 16-column loads two chunks ahead (now; 144 -> 112 registers) are equal.
+//   * 32-column loads one batch ahead (this kernel) and 16-column loads two chunks ahead (the pair template; 144 ->
+//     112 registers) are equal;
+//   * the single-CTA instance of the pair template is 4 % slower than this hand-specialised kernel (same-run A/B,
+//     although nothing that runs differs in the source), and a run-time test of the debug option in the tile loop
+//     costs another 1.4 %: the default kernel is kept as its own code, the debug modes are template instances.
 // Chunks of 32 columns, N = 128 MMAs and polling barriers from all threads measured equal or slower in r01e;
 // chunks of 8 (kVC) halve the saved bytes but add instructions: faster at 1024 keypoints, slower at 8192.
 // See DESIGN.md.
@@ -608,6 +612,76 @@ constexpr int kFlagged    = -2;                           // top2_idx[row][0] of
 constexpr int kVC   = 16;                // columns per chunk of the V-space epilogue (8 or 16)
 constexpr int kVCps = kBlockT / kVC;     // chunks per tile
 constexpr int kVClog = kVC == 8 ? 5 : 4; // log2(kVCps)
+// ---- single-CTA kernel (default).  Kept as its own, non-templated code: the instance of the CTA-pair template below
+// for one CTA compiled to a 4 % slower kernel (same-run A/B, r01g), although the source differs in nothing that runs.
+struct VCfg {
+    static constexpr int threads   = 384;
+    static constexpr int q_off     = 0;                                // 2 x 32 KB
+    static constexpr int t_off     = q_off + 2 * kQBytes;              // kStages x 32 KB
+    static constexpr int e_off     = t_off + kStages * kTileBytes;     // kStages x 8 KB
+    static constexpr int a_off     = e_off + kStages * kECodeBytes;    // 4 KB: query-side fifth K block
+    static constexpr int slot_off  = a_off + 128 * 32;                 // [slot 2][part 4][row 256] x 16 B
+    static constexpr int part_stride = 256 * 16;
+    static constexpr int slot_stride = (kVC / 4) * part_stride;
+    static constexpr int pb_bytes  = (EVZ_MAX_KP / kBlockT) * 32;      // norm parity bitmap of one train frame
+    static constexpr int pb_off    = slot_off + 2 * slot_stride;       // 2 x pb_bytes, alternating per item
+    static constexpr int item_off  = pb_off + 2 * pb_bytes;
+    static constexpr int bar_off   = item_off + 2 * static_cast<int>(sizeof(Item));
+    static constexpr int n_bars    = 2 * kStages + 2 + 2 + 2 + 2;
+    static constexpr int tmem_off  = bar_off + n_bars * 8;
+    static constexpr int total     = tmem_off + 16;
+    static constexpr int smem_bytes = total + 1024;
+    static_assert(smem_bytes <= 227 * 1024, "V-space match kernel shared memory exceeds 227 KB");
+};
+
+// one chunk of kVC raw accumulator values: chunk key, sorted top-3 update, predicated save
+__device__ __forceinline__ void vchunk(const uint32_t* r, uint32_t tagc, uint32_t mul, uint32_t& M1, uint32_t& M2,
+                                       uint32_t& M3, uint32_t& sec, uint32_t sum) {
+    uint32_t cm;
+    if (kVC == 16) {
+        const uint32_t a = __vimax3_u32(r[0], r[1], r[2]), b = __vimax3_u32(r[3], r[4], r[5]), c = __vimax3_u32(r[6], r[7], r[8]);
+        const uint32_t d = __vimax3_u32(r[9], r[10], r[11]), e = __vimax3_u32(r[12], r[13], r[14]);
+        cm = max(__vimax3_u32(a, b, c), __vimax3_u32(d, e, r[15]));
+    } else {
+        cm = __vimax3_u32(__vimax3_u32(r[0], r[1], r[2]), __vimax3_u32(r[3], r[4], r[5]), max(r[6], r[7]));
+    }
+    uint32_t cmk;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(cmk) : "r"(cm), "r"(mul), "r"(tagc));
+    // the next store address goes to a different register (early clobber): overwriting `sec` in place would wait
+    // for the stores to have read it (write-after-read on the short scoreboard, ~35 clk per chunk)
+    const uint32_t alt = sum - sec;
+    uint32_t nsec;
+    if (kVC == 16) {
+        asm volatile("{\n\t.reg .pred p1, p2;\n\t"
+                     "setp.gt.u32 p2, %2, %4;\n\t"
+                     "setp.gt.u32 p1, %2, %3;\n\t"
+                     "@p2 st.shared.v4.b32 [%1], {%6, %7, %8, %9};\n\t"
+                     "@p2 st.shared.v4.b32 [%1+%22], {%10, %11, %12, %13};\n\t"
+                     "@p2 st.shared.v4.b32 [%1+2*%22], {%14, %15, %16, %17};\n\t"
+                     "@p2 st.shared.v4.b32 [%1+3*%22], {%18, %19, %20, %21};\n\t"
+                     "selp.u32 %0, %5, %1, p1;\n\t}"
+                     : "=&r"(nsec) : "r"(sec), "r"(cmk), "r"(M1), "r"(M2), "r"(alt),
+                       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                       "r"(r[8 % kVC]), "r"(r[9 % kVC]), "r"(r[10 % kVC]), "r"(r[11 % kVC]), "r"(r[12 % kVC]), "r"(r[13 % kVC]),
+                       "r"(r[14 % kVC]), "r"(r[15 % kVC]), "n"(VCfg::part_stride) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p1, p2;\n\t"
+                     "setp.gt.u32 p2, %2, %4;\n\t"
+                     "setp.gt.u32 p1, %2, %3;\n\t"
+                     "@p2 st.shared.v4.b32 [%1], {%6, %7, %8, %9};\n\t"
+                     "@p2 st.shared.v4.b32 [%1+%14], {%10, %11, %12, %13};\n\t"
+                     "selp.u32 %0, %5, %1, p1;\n\t}"
+                     : "=&r"(nsec) : "r"(sec), "r"(cmk), "r"(M1), "r"(M2), "r"(alt),
+                       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                       "n"(VCfg::part_stride) : "memory");
+    }
+    sec = nsec;
+    const uint32_t t = min(M1, cmk), u = __vimin3_u32(M1, M2, cmk);
+    M1 = max(M1, cmk);
+    M3 = max(M3, u);
+    M2 = max(M2, t);
+}
+
 // kCtas = 1: one CTA per work item (256 query rows).  kCtas = 2: a CTA pair (cta_group::2) shares every train
 // tile -- each CTA stages half of it (128 rows + their 4 KB of the fifth K block) and drains its own 256 query rows.
 template <int kCtas>
@@ -704,6 +778,270 @@ __device__ __forceinline__ void keep_alive16(const uint32_t* r) {
                        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
 }
 
+// one accumulator row (256 columns): 8 batches of 32 columns, TMEM loads one batch ahead; the accumulator is
+// handed back to the MMA warp as soon as its last column is in registers
+__device__ __forceinline__ void drain_v(uint32_t taddr, uint32_t mul, uint32_t& M1, uint32_t& M2, uint32_t& M3,
+                                        uint32_t& sec, uint32_t sum, uint64_t* acc_empty, int lane) {
+    uint32_t r[2][32];
+    tmem_ld_32x32b_x32(taddr, r[0]);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        tmem_ld_wait_dep(r[b & 1]);
+        if (b + 1 < 8) {
+            tmem_ld_32x32b_x32(taddr + (b + 1) * 32, r[(b + 1) & 1]);
+        } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+#pragma unroll
+        for (int c = 0; c < 32 / kVC; ++c) vchunk(&r[b & 1][kVC * c], 254 - (32 / kVC) * b - c, mul, M1, M2, M3, sec, sum);
+        keep_alive16(&r[b & 1][0]);
+        keep_alive16(&r[b & 1][16]);
+    }
+}
+
+// kDbg (EVZ_OPT_MATCH_DEBUG, measurement only): 1 = accumulators released undrained, 2 = TMEM loads only; the
+// production instance is kDbg = 0 (a run-time test in the tile loop costs 1.4 %).
+template <int kDbg>
+__global__ void __launch_bounds__(VCfg::threads, 1)
+match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args) {
+    using Cfg = VCfg;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* q_s = smem + Cfg::q_off;
+    uint8_t* t_s = smem + Cfg::t_off;
+    uint8_t* e_s = smem + Cfg::e_off;
+    uint8_t* a_s = smem + Cfg::a_off;
+    Item* item_s = reinterpret_cast<Item*>(smem + Cfg::item_off);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::bar_off);
+    uint64_t* full = bars;                       // [kStages] train tile + its fifth K block landed (TMA tx)
+    uint64_t* empty = full + kStages;            // [kStages] MMA commit
+    uint64_t* q_full = empty + kStages;          // [2] query block landed + item descriptor published
+    uint64_t* q_empty = q_full + 2;              // [2] MMA commit + 8 epilogue warps
+    uint64_t* acc_full = q_empty + 2;            // [2] accumulator (= query sub-tile) ready (MMA commit)
+    uint64_t* acc_empty = acc_full + 2;          // [2] accumulator drained (4 epilogue warps each)
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + Cfg::tmem_off);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1 + 8);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_s, 512);
+        tmem_relinquish();
+    }
+    if (warp == 3) {
+        // query-side fifth K block: every row = (255 x 30, 1, 0), no-swizzle core-matrix layout
+        for (int i = lane; i < 256; i += 32) {
+            const bool second = (i >> 3) & 1;          // [group 16][k half 2][row 8] x 16 B
+            reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, second ? 0x0001FFFFu : 0xFFFFFFFFu);
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+    const int n_items = *args.n_items;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------- TMA producer (polling waits, single thread)
+        if (lane == 0) {
+            uint32_t stage = 0, sphase = 0, qi = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const Item im = load_item(args, it);
+                const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+                ++qi;
+                mbar_wait_spin(&q_empty[qb], qph ^ 1);
+                item_s[qb] = im;
+                if (im.n_tiles == 0) { mbar_arrive(&q_full[qb]); continue; }
+                mbar_arrive_expect_tx(&q_full[qb], kQBytes + im.n_tiles * 32);
+                tma_load_2d(q_s + qb * kQBytes, &tmap, 0, im.q_row0, &q_full[qb]);
+                bulk_load_1d(smem + Cfg::pb_off + qb * Cfg::pb_bytes, args.pbits + static_cast<size_t>(im.t_row0 >> 8) * 8,
+                             im.n_tiles * 32, &q_full[qb]);
+                const uint8_t* ecode = args.ecode + static_cast<size_t>(im.t_row0 >> 8) * kECodeBytes;
+                for (int n = 0; n < im.n_tiles; ++n) {
+                    // the ring is only kStages deep: pull the tile that will be loaded kStages iterations from now
+                    // into L2 already, so that its TMA load is an L2 hit
+                    if (n + kStages < im.n_tiles) {
+                        tma_prefetch_2d(&tmap, 0, im.t_row0 + (n + kStages) * kBlockT);
+                        bulk_prefetch_1d(ecode + static_cast<size_t>(n + kStages) * kECodeBytes, kECodeBytes);
+                    }
+                    mbar_wait_spin(&empty[stage], sphase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], kTileBytes + kECodeBytes);
+                    tma_load_2d(t_s + stage * kTileBytes, &tmap, 0, im.t_row0 + n * kBlockT, &full[stage]);
+                    bulk_load_1d(e_s + stage * kECodeBytes, ecode + static_cast<size_t>(n) * kECodeBytes, kECodeBytes, &full[stage]);
+                    if (++stage == kStages) { stage = 0; sphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            // accumulator = query sub-tile.  The waits of this single thread poll: a tcgen05.mma issue blocks
+            // until the tensor pipe accepts it, so the pipe only stays fed while this thread is never late,
+            // and a suspended try_wait wakes up late.
+            constexpr uint32_t idesc = umma_idesc_u8(128, kBlockT);
+            const uint64_t da_e = umma_desc_nosw(smem_u32(a_s), 128, 256);
+            uint32_t stage = 0, sphase = 0, qi = 0, gs[2] = {0, 0};
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+                ++qi;
+                mbar_wait_spin(&q_full[qb], qph);
+                const int n_tiles = item_s[qb].n_tiles, n_sub = item_s[qb].n_sub;
+                const uint32_t q_addr = smem_u32(q_s + qb * kQBytes);
+                for (int n = 0; n < n_tiles; ++n) {
+                    mbar_wait_spin(&full[stage], sphase);
+                    const uint32_t t_addr = smem_u32(t_s + stage * kTileBytes);
+                    const uint64_t db_e = umma_desc_nosw(smem_u32(e_s + stage * kECodeBytes), 128, 256);
+                    for (int sub = 0; sub < n_sub; ++sub) {
+                        const uint32_t aph = gs[sub]++ & 1;
+                        mbar_wait_spin(&acc_empty[sub], aph ^ 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int k = 0; k < kRowBytes / 32; ++k) {
+                            const uint64_t da = umma_desc_sw128(q_addr + sub * (128 * kRowBytes) + k * 32);
+                            const uint64_t db = umma_desc_sw128(t_addr + k * 32);
+                            umma_i8(tmem_base + sub * kBlockT, da, db, idesc, k > 0 ? 1u : 0u);
+                        }
+                        umma_i8(tmem_base + sub * kBlockT, da_e, db_e, idesc, 1u);
+                        umma_commit(&acc_full[sub]);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == kStages) { stage = 0; sphase ^= 1; }
+                }
+                umma_commit(&q_empty[qb]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------- epilogue
+        const int grp = (warp - 4) >> 2;                       // query sub-tile = accumulator
+        const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
+        const int row = grp * 128 + quarter * 32 + lane;       // query row within the block
+        const uint32_t slot_a = smem_u32(smem + Cfg::slot_off) + row * 16, slot_b = slot_a + Cfg::slot_stride;
+        const uint32_t sum = slot_a + slot_b;
+        const uint32_t taddr = tmem_base + grp * kBlockT + (static_cast<uint32_t>(quarter * 32) << 16);
+        uint32_t g = 0, qi = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+            ++qi;
+            mbar_wait(&q_full[qb], qph);
+            const Item im = item_s[qb];
+            if (grp < im.n_sub) {
+                const int qkey = __ldg(args.ckey + im.q_row0 + row);
+                // sorted top-3 of chunk keys, the slot that holds the second-best chunk, and the position
+                // (tile * 16 + chunk) of the chunks in the best / second-best slot
+                uint32_t M1 = 0, M2 = 0, M3 = 0, sec = slot_b;
+                int Tb = -1, Ts = -1;
+                for (int n = 0; n < im.n_tiles; ++n) {
+                    // keys of earlier tiles beat every key of this tile with the same V (lowest index wins)
+                    M1 |= 255u; M2 |= 255u; M3 |= 255u;
+                    const uint32_t o1 = M1, o2 = M2;
+                    mbar_wait(&acc_full[grp], g & 1);
+                    tc_fence_after();
+                    if constexpr (kDbg != 0) {
+                        if (kDbg == 2) {                  // every column loaded and waited for, no arithmetic, no saves
+                            uint32_t r[2][32];
+                            tmem_ld_32x32b_x32(taddr, r[0]);
+#pragma unroll
+                            for (int b = 0; b < 8; ++b) {
+                                tmem_ld_wait_dep(r[b & 1]);
+                                if (b + 1 < 8) tmem_ld_32x32b_x32(taddr + (b + 1) * 32, r[(b + 1) & 1]);
+                                keep_alive16(&r[b & 1][0]);
+                                keep_alive16(&r[b & 1][16]);
+                            }
+                        }
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&acc_empty[grp]);
+                        ++g;
+                        continue;
+                    }
+                    drain_v(taddr, args.mul256, M1, M2, M3, sec, sum, &acc_empty[grp], lane);
+                    ++g;
+                    const int nTb = M1 == o1 ? Tb : n * kVCps + 254 - static_cast<int>(M1 & 255u);
+                    Ts = (M1 != o1 && M2 == o1) ? Tb : (M2 == o2 ? Ts : n * kVCps + 254 - static_cast<int>(M2 & 255u));
+                    Tb = nTb;
+                }
+                // exact evaluation of the two saved chunks: ||t||^2 - 2 q.t = 2 (hmax + 1 - V) + parity, packed
+                // with the ordinal of the column among the 32 candidates (the slot with the lower position
+                // first), so that a signed min is the lexicographic (distance, index) minimum.  Padding
+                // columns have V = 0, i.e. a distance above every real column: they sort last by themselves.
+                const int hm1 = im.pad + 1;
+                const bool best_first = Ts < 0 || Tb < Ts;
+                int k[2 * kVC];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int T = s == 0 ? Tb : Ts;
+                    const uint32_t sa = s == 0 ? sum - sec : sec;
+                    if (T >= 0) {
+                        const int base = (T >> kVClog) * kBlockT + (T & (kVCps - 1)) * kVC;
+                        const int cs = (2 * hm1) * 256 + ((s == 0) == best_first ? 0 : kVC);
+                        uint32_t ps;                       // norm parity of the chunk's columns, moved to bits 8..
+                        if (kVC == 16) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ps) : "r"(smem_u32(smem + Cfg::pb_off) + qb * Cfg::pb_bytes + (base >> 3)));
+                        else           asm volatile("ld.shared.u8 %0, [%1];" : "=r"(ps) : "r"(smem_u32(smem + Cfg::pb_off) + qb * Cfg::pb_bytes + (base >> 3)));
+                        ps <<= 8;
+#pragma unroll
+                        for (int part = 0; part < kVC / 4; ++part) {
+                            const int4 v = lds128(sa + part * Cfg::part_stride);
+                            k[s * kVC + part * 4 + 0] = mad_key(v.x, args.neg512, cs) + (((ps >> (part * 4 + 0)) & 256) + part * 4 + 0);
+                            k[s * kVC + part * 4 + 1] = mad_key(v.y, args.neg512, cs) + (((ps >> (part * 4 + 1)) & 256) + part * 4 + 1);
+                            k[s * kVC + part * 4 + 2] = mad_key(v.z, args.neg512, cs) + (((ps >> (part * 4 + 2)) & 256) + part * 4 + 2);
+                            k[s * kVC + part * 4 + 3] = mad_key(v.w, args.neg512, cs) + (((ps >> (part * 4 + 3)) & 256) + part * 4 + 3);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kVC; ++i) k[s * kVC + i] = INT_MAX;
+                    }
+                }
+                int m1 = INT_MAX, m2 = INT_MAX;
+#pragma unroll
+                for (int i = 0; i < kVC; ++i) top2_pair(k[2 * i], k[2 * i + 1], m1, m2);
+                const int base_b = Tb >= 0 ? (Tb >> kVClog) * kBlockT + (Tb & (kVCps - 1)) * kVC : 0;
+                const int base_s = Ts >= 0 ? (Ts >> kVClog) * kBlockT + (Ts & (kVCps - 1)) * kVC : 0;
+                const int base_lo = best_first ? base_b : base_s, base_hi = best_first ? base_s : base_b;
+                const int c1 = ((m1 & kVC) ? base_hi : base_lo) + (m1 & (kVC - 1)), c2 = ((m2 & kVC) ? base_hi : base_lo) + (m2 & (kVC - 1));
+                const int I1 = (m1 != INT_MAX && c1 < im.nt) ? c1 : -1, I2 = (m2 != INT_MAX && c2 < im.nt) ? c2 : -1;
+                const int V1 = m1 >> 8, V2 = m2 >> 8;
+                // every column outside the two slots has V <= V3, i.e. ||t||^2 - 2 q.t >= 2 (hmax + 1 - V3)
+                const bool third = M3 > 255u;
+                const int bound = 2 * (hm1 - static_cast<int>(M3 >> 8));
+                const bool flagged = third && (I2 < 0 || V2 >= bound);
+                if (row < im.nq_left) {
+                    const int qn = qkey >> 8;
+                    const int64_t o_row = static_cast<int64_t>(im.out_row0) + row;
+                    int2 oi, od;
+                    oi.x = flagged ? kFlagged : I1; od.x = I1 >= 0 ? V1 + qn : -1;
+                    oi.y = I2;                      od.y = I2 >= 0 ? V2 + qn : -1;
+                    reinterpret_cast<int2*>(args.top2_idx)[o_row] = oi;
+                    reinterpret_cast<int2*>(args.top2_d2)[o_row] = od;
+                    if (flagged) {
+                        const int pos = atomicAdd(args.fix_count, 1);
+                        if (pos < args.fix_capacity) args.fix_list[pos] = it * 256 + row;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_empty[qb]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+
+// ---- CTA-pair template (EVZ_OPT_MATCH_VARIANT = 7)
 // one accumulator row (256 columns) in 16 loads of one chunk (16 columns) each, two loads ahead of the chunk being
 // processed, into four 16-register buffers: the load for chunk c + 2 overwrites the registers of chunk c - 2, whose
 // (predicated) stores were issued a whole chunk ago.  With 32-column loads one batch ahead, every load had to wait
@@ -1238,7 +1576,9 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
         a.ecode = ecode;
         static bool v_attr_set = false;
         if (!v_attr_set) {
-            EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfgT<1>::smem_bytes));
+            EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
+            EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
+            EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfgT<2>::smem_bytes));
             v_attr_set = true;
         }
@@ -1264,8 +1604,12 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
             cfg.attrs = at;
             cfg.numAttrs = 1;
             EVZ_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, evz::match_top2_vkernel_t<2>, h->tmap, h->tmap_half, a));
+        } else if (h->opt_match_debug == 1) {
+            evz::match_top2_vkernel<1><<<h->sm_count, evz::VCfg::threads, evz::VCfg::smem_bytes, st>>>(h->tmap, a);
+        } else if (h->opt_match_debug == 2) {
+            evz::match_top2_vkernel<2><<<h->sm_count, evz::VCfg::threads, evz::VCfg::smem_bytes, st>>>(h->tmap, a);
         } else {
-            evz::match_top2_vkernel_t<1><<<h->sm_count, evz::VCfgT<1>::threads, evz::VCfgT<1>::smem_bytes, st>>>(h->tmap, h->tmap_half, a);
+            evz::match_top2_vkernel<0><<<h->sm_count, evz::VCfg::threads, evz::VCfg::smem_bytes, st>>>(h->tmap, a);
         }
         EVZ_LAUNCH_CHECK(h);
         if (tev) EVZ_CUDA_CHECK(h, cudaEventRecord(tev[1], st));

@@ -593,7 +593,7 @@ __global__ void build_items_kernel(const int32_t* n_kp, const int32_t* pair_q, i
 //     warp-uniform vote + branch when no lane saves is 18 % SLOWER in a same-run A/B (per chunk, or after both chunks of a
 //     batch), also at 8192 keypoints where 60 % of the chunks have no saving lane;
 //   * it is not the shared-memory data pipe (the r01e reading): CTA pairs (cta_group::2, variant 7: half the TMA
-//     writes, a third less operand fetch per SM) run at parity, not faster;
+//     writes, a third less operand fetch per SM) are 5 % slower than this kernel, not faster;
 //   * it is not the accumulator hand-off either: eight warps per accumulator (column halves, merged at the end
 //     of the item; possible with the smaller rings of the pair layout) are 25 % slower with 8 epilogue warps (all
 //     of them wait for the same accumulator) and 9 % slower with 16;

@@ -184,10 +184,21 @@ __device__ __forceinline__ void ldl8_solve(const Ldl8& f, const double (&b)[8], 
 //   sums[29] S = sum r^2, sums[30] = max |r|
 // (explicit fma(): this file is compiled with --fmad=false for the bit-exact kernels, but the refit only has
 // to reach the same optimum -- shared products and fused accumulation halve its f64 instruction count)
+// 1 / x for the refit: single-precision seed + two Newton steps in double (full double accuracy for |x| in the
+// float range; the denominator of a homography over image coordinates is ~1).  The IEEE division it replaces is
+// ~15 instructions per point; the refit only has to reach the same optimum, not the same bits.
+__device__ __forceinline__ double refit_rcp(double x) {
+    float rf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rf) : "f"(static_cast<float>(x)));
+    double r = static_cast<double>(rf);
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
 __device__ __forceinline__ void lm_point(const double* h, const float4 pt, double* s) {
     const double Mx = pt.x, My = pt.y;
     double ww = fma(h[6], Mx, fma(h[7], My, 1.0));
-    ww = fabs(ww) > DBL_EPSILON ? 1.0 / ww : 0.0;
+    ww = fabs(ww) > DBL_EPSILON ? refit_rcp(ww) : 0.0;
     const double xi = fma(h[0], Mx, fma(h[1], My, h[2])) * ww;
     const double yi = fma(h[3], Mx, fma(h[4], My, h[5])) * ww;
     const double rx = xi - pt.z, ry = yi - pt.w;
@@ -239,21 +250,28 @@ __device__ void lm_accumulate(const double* h, const float4* pts, const uint8_t*
     for (int i = 0; i < kNSums; ++i) s[i] = 0.0;
     for (int i = threadIdx.x; i < m; i += blockDim.x) if (msk[i]) lm_point(h, pts[i], s);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // warp reduction of the 30 sums as a transposing butterfly: at every step a lane keeps one half of its values
+    // and trades the other half, so that lane i ends up with the warp total of sum i (31 exchanges instead of
+    // 30 x 5); the maximum (s[30]) is reduced on its own
+    double mx = s[30];
 #pragma unroll
-    for (int i = 0; i < 31; ++i) {
-        double t = s[i];
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffff, mx, o));
+    double v[32];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double u = __shfl_xor_sync(0xffffffff, t, o);
-            t = (i == 30) ? fmax(t, u) : t + u;
+    for (int i = 0; i < 30; ++i) v[i] = s[i];
+    v[30] = 0.0; v[31] = 0.0;
+#pragma unroll
+    for (int n = 16; n > 0; n >>= 1) {
+        const bool up = (lane & n) != 0;
+#pragma unroll
+        for (int i = 0; i < n; ++i) {
+            const double keep = up ? v[i + n] : v[i];
+            const double send = up ? v[i] : v[i + n];
+            v[i] = keep + __shfl_xor_sync(0xffffffff, send, n);
         }
-        s[i] = t;
     }
     __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < 31; ++i) L.wsum[warp][i] = s[i];
-    }
+    if (lane < 31) L.wsum[warp][lane] = lane == 30 ? mx : v[0];
     __syncthreads();
     if (threadIdx.x < 31) {
         double t = L.wsum[0][threadIdx.x];

@@ -198,3 +198,27 @@ def test_streaming_json_writers_match_json_dump(tmp_path, bundled):
     assert out.getvalue() == json.dumps(refc)
     fr2, c2, xy2 = formats.load_coordinates_arrays(io.StringIO(out.getvalue()))
     assert np.array_equal(fr2, np.arange(1, 501)) and np.array_equal(c2, counts) and np.array_equal(xy2, xy)
+
+
+def test_bench_flann_agreement_rates():
+    """bench.py's reported-only FLANN agreement (north_star): fed with the exact brute-force result it must report
+    rates in [0, 1], near-perfect survivor agreement on descriptor-like data, and exactly 1.0 against itself-like
+    input where FLANN is exact (tiny train sets are searched exhaustively by the KD-tree with checks >= size)."""
+    import importlib.util
+    from evenvizion_b200 import synth
+    from oracle import matching
+    spec = importlib.util.spec_from_file_location("evz_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ch = synth.make_chain(3, 384, seed=5, device="cpu")
+    d = ch["desc"]
+    gi, gs = [], []
+    for k in range(2):
+        idx, d2 = matching.knn_top2(d[k + 1].numpy(), d[k].numpy())
+        gi.append(idx[:, 0]); gs.append(matching.ratio_survivors(idx, d2))
+    out = bench.flann_agreement(d, gi, gs)
+    assert out["pairs"] == 2 and 0.5 <= out["top1"] <= 1.0 and out["survivors_jaccard"] >= 0.95
+    small = torch.from_numpy(np.random.default_rng(1).integers(0, 256, (2, 24, 128)).astype(np.uint8))
+    idx, d2 = matching.knn_top2(small[1].numpy(), small[0].numpy())
+    out = bench.flann_agreement(small, [idx[:, 0]], [matching.ratio_survivors(idx, d2)])
+    assert out["top1"] == 1.0 and out["survivors_jaccard"] in (0.0, 1.0)

@@ -1041,7 +1041,8 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
 }
 
 
-// ---- CTA-pair template (EVZ_OPT_MATCH_VARIANT = 7)
+// ---- CTA-pair template (EVZ_OPT_MATCH_VARIANT = 7).  Only kCtas = 2 is instantiated; the kCtas == 1 branches are the
+// default kernel's code path (they are how the 4 % of the note above were measured) and compile to nothing.
 // one accumulator row (256 columns) in 16 loads of one chunk (16 columns) each, two loads ahead of the chunk being
 // processed, into four 16-register buffers: the load for chunk c + 2 overwrites the registers of chunk c - 2, whose
 // (predicated) stores were issued a whole chunk ago.  With 32-column loads one batch ahead, every load had to wait

@@ -356,10 +356,9 @@ extern "C" int evz_static_filter(evz_handle* h, const float* pts, const int32_t*
     EVZ_REQUIRE(h, pts && off && cnt && H && status && out_pts && out_cnt && best_r && flags, "null pointer");
     if (n_pairs <= 0) return EVZ_OK;
     const int smem = EVZ_MAX_KP * 2 + evz::kSfWindow * 8;
-    static bool attr = false;
-    if (!attr) {
+    if (!h->attr_static) {
         EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::static_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
+        h->attr_static = true;
     }
     evz::static_filter_kernel<<<n_pairs, 256, smem, static_cast<cudaStream_t>(stream)>>>(pts, off, cnt, H, status, out_pts, out_cnt, best_r, flags, r_out);
     EVZ_LAUNCH_CHECK(h);

@@ -25,7 +25,10 @@ struct evz_handle {
     const void* tmap_ptr = nullptr;
     int64_t tmap_rows = 0;
     evz_encode_tiled_fn encode = nullptr;
-    bool match_attr_set = false;
+    // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remembered per handle, not per process
+    unsigned attr_match = 0;       // bit per match kernel instance
+    bool attr_static = false, attr_canon = false;
+    int attr_filter = 0, attr_score = 0, attr_refit = 0;
     // options (evz_set_option)
     int opt_ransac_exact = 0;
     int opt_ransac_no_prune = 0;

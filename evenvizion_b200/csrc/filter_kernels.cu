@@ -235,10 +235,9 @@ extern "C" int evz_ingest(evz_handle* h, const void* raw_desc, int raw_is_f32, i
     evz::ingest_pack_kernel<<<n_frames, 256, 0, st>>>(raw_desc, raw_is_f32, d, raw_coords, raw_off, row_off, desc, ckey, coords, bad_count);
     EVZ_LAUNCH_CHECK(h);
     const int table = 32768;    // >= 2 * kMaxKpSmem
-    static bool attr = false;
-    if (!attr) {
+    if (!h->attr_canon) {
         EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::ingest_canon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, table * 4));
-        attr = true;
+        h->attr_canon = true;
     }
     evz::ingest_canon_kernel<<<n_frames, 256, table * 4, st>>>(coords, raw_off, row_off, canon, table);
     EVZ_LAUNCH_CHECK(h);
@@ -262,10 +261,9 @@ extern "C" int evz_filter_matches(evz_handle* h, const int32_t* top2_idx, const 
     if (n_pairs <= 0) return EVZ_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int smem = 16 * (max_kp > 0 ? max_kp : 1);
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
+    if (smem > h->attr_filter) {
         EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::filter_matches_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
+        h->attr_filter = smem;
     }
     evz::FilterArgs a{top2_idx, top2_d2, coords, canon, row_off, n_kp, pair_q, pair_t, out_off, ratio, min_matching_pts,
                       surv, m_idx, m_pts, m_cnt, n_filtered, status};

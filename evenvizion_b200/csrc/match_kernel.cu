@@ -1547,11 +1547,11 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
 #define EVZ_MATCH_LAUNCH(CH, EW)                                                                                         \
     do {                                                                                                                 \
         using Cfg = evz::MatchCfg<CH, EW>;                                                                               \
-        static bool attr_set = false;                                                                                    \
-        if (!attr_set) {                                                                                                 \
+        constexpr unsigned kBit = CH == 0 ? 1u : CH == 8 ? 2u : 4u;                                                      \
+        if (!(h->attr_match & kBit)) {                                                                                   \
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_kernel<CH, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                                    Cfg::smem_bytes));                                                    \
-            attr_set = true;                                                                                             \
+            h->attr_match |= kBit;                                                                                       \
         }                                                                                                                \
         evz::match_top2_kernel<CH, EW><<<h->sm_count, Cfg::threads, Cfg::smem_bytes, st>>>(h->tmap, a);                  \
     } while (0)
@@ -1575,13 +1575,12 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
         EVZ_LAUNCH_CHECK(h);
         a.pair_hmax = pair_hmax;
         a.ecode = ecode;
-        static bool v_attr_set = false;
-        if (!v_attr_set) {
+        if (!(h->attr_match & 8u)) {
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfgT<2>::smem_bytes));
-            v_attr_set = true;
+            h->attr_match |= 8u;
         }
         cudaEvent_t* tev = nullptr;
         if (h->opt_time_match) {

@@ -956,14 +956,13 @@ extern "C" int evz_find_homography(evz_handle* h, const float* pts, const int32_
     EVZ_REQUIRE(h, n_hyp <= 65535, "n_hyp must be below 65536");
     const int smem_score = max_cnt * 16 + 8 * n_hyp + 16;
     const int smem_refit = max_cnt * 17 + 16;
-    static int attr_score = 0, attr_refit = 0;
-    if (smem_score > attr_score) {
+    if (smem_score > h->attr_score) {
         EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::ransac_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_score));
-        attr_score = smem_score;
+        h->attr_score = smem_score;
     }
-    if (smem_refit > attr_refit) {
+    if (smem_refit > h->attr_refit) {
         EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::ransac_refit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_refit));
-        attr_refit = smem_refit;
+        h->attr_refit = smem_refit;
     }
     const float t = static_cast<float>(thresh * thresh);
     evz::FhArgs a{pts, off, cnt, pre_H, n_hyp, seed, pair_id_base, level, t, min_inlier_frac, fail_status,

@@ -29,7 +29,9 @@ namespace evz {
 constexpr int kRsThreads = 256;   // scoring kernel
 constexpr int kRfThreads = 64;    // refit kernel
 constexpr int kHpt = 4;           // hypotheses scored concurrently per thread
-constexpr int kProbe = 64;        // hypotheses of the level-2 probe row (see ransac_score_kernel)
+constexpr int kProbe = 64;        // hypotheses of the level-2 probe (see ransac_score_kernel)
+constexpr int kProbe0 = 16;       // ... of which this many go first
+constexpr int kStagesMax = 6;     // stages of the level-1 staged scoring
 constexpr int kLmMaxIters = 20;   // OpenCV uses 10 from a DLT start; we start from the 4-point model
 constexpr int kNSums = 32;        // 21 JtJ + 8 Jtr + S + max|r| (+1 pad)
 
@@ -344,11 +346,19 @@ __device__ __forceinline__ void fused_thresholds(const float (&h)[8], float cmax
 // partial counts (sure-in, sure-out) are parked in lo_s / hi_s.  SUFFIX: matches [i0, m) on top of the parked
 // partial counts, final bounds.  (Two-phase scoring, see ransac_score_kernel.)
 struct PtRange { int i0, i1, mode; };
-constexpr int kFull = 0, kPrefix = 1, kSuffix = 2;
+// kMid: a middle stage of the staged scoring -- starts from the parked partial counts and parks them again
+constexpr int kFull = 0, kPrefix = 1, kSuffix = 2, kMid = 3;
 constexpr int kLead = 32;                    // hypotheses of the fully scored leading batch of the two-phase scoring
 
+// the four sampled correspondences of a hypothesis: sample indices refer to the caller's order, pos[] maps them to
+// where the point lives in shared memory (identity until the level-1 partition by the leader's residuals)
+__device__ __forceinline__ void load_sample(const float4* pts, const uint16_t* pos, const int (&idx)[4], float4 (&q)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) q[k] = pts[pos[idx[k]]];
+}
+
 template <int NJ, bool kCheckDen>
-__device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, const uint16_t* vlist,
+__device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, const uint16_t* pos, const uint16_t* vlist,
                                            uint16_t* lo_s, uint16_t* hi_s, int s0, int n_valid, int m, float cmax,
                                            uint32_t pair_level, int* cut, const PtRange rg) {
     const int tid = threadIdx.x;
@@ -368,14 +378,15 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
         if (slot < n_valid && static_cast<int>(vlist[slot]) < cutv) {
             int idx[4];
             sample4(a.seed, pair_level, static_cast<uint32_t>(vlist[slot]), m, idx);
-            const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
+            float4 q[4];
+            load_sample(pts, pos, idx, q);
             double H[9];
             solve4(q, H);
 #pragma unroll
             for (int i = 0; i < 8; ++i) hf[j][i] = static_cast<float>(H[i]);
             fused_thresholds(hf[j], cmax, a.thresh2, a.exact_only != 0, tlo[j], thi[j]);
             any_live = true;
-            if (rg.mode == kSuffix) { lo[j] = lo_s[slot]; out[j] = hi_s[slot]; }
+            if (rg.mode == kSuffix || rg.mode == kMid) { lo[j] = lo_s[slot]; out[j] = hi_s[slot]; }
         }
     }
     const int i_end = __any_sync(0xffffffff, any_live) ? rg.i1 : 0;   // a warp without live hypotheses skips the matches
@@ -402,7 +413,7 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
     for (int j = 0; j < NJ; ++j) {
         const int slot = s0 + j * kRsThreads + tid;
         if (thi[j] > -INFINITY) {
-            if (rg.mode == kPrefix) {
+            if (rg.mode == kPrefix || rg.mode == kMid) {
                 lo_s[slot] = static_cast<uint16_t>(lo[j]); hi_s[slot] = static_cast<uint16_t>(out[j]);
             } else {
                 lo_s[slot] = static_cast<uint16_t>(lo[j]); hi_s[slot] = static_cast<uint16_t>(m - out[j]);
@@ -420,11 +431,11 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
 // L rounded up to a power of two >= 32, slice = tid / Lp of kRsThreads / Lp slices, and every slice scores
 // a strided share of the matches; partial counts meet in shared memory.  Same classification per
 // evaluation as score_batch<.., true>, so the bounds are identical.
-__device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4* pts, const uint16_t* vlist,
+__device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4* pts, const uint16_t* pos, const uint16_t* vlist,
                                                   uint16_t* lo_s, uint16_t* hi_s, int* part, int* lbest, int* cut, int r0, int L, int m,
                                                   float cmax, uint32_t pair_level, const PtRange rg) {
     const int tid = threadIdx.x;
-    int Lp = 32;
+    int Lp = 16;
     while (Lp < L) Lp <<= 1;
     const int slices = kRsThreads / Lp;
     const int k = tid & (Lp - 1), slice = tid / Lp;
@@ -436,7 +447,8 @@ __device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4*
     if (live) {
         int idx[4];
         sample4(a.seed, pair_level, static_cast<uint32_t>(vlist[r0 + k]), m, idx);
-        const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
+        float4 q[4];
+        load_sample(pts, pos, idx, q);
         double H[9];
         solve4(q, H);
 #pragma unroll
@@ -447,8 +459,7 @@ __device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4*
     __syncthreads();
     int lo = 0, out = 0;
     const int i_end = __any_sync(0xffffffff, live) ? rg.i1 : 0;      // a warp without live hypotheses skips the matches
-    for (int i = rg.i0 + slice; i < i_end; i += slices) {
-        const float4 pt = pts[i];
+    auto eval = [&](const float4 pt) {
         const float den = __fmaf_rn(hf[6], pt.x, __fmaf_rn(hf[7], pt.y, 1.f));
         float ww;
         asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(ww) : "f"(den));
@@ -460,14 +471,22 @@ __device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4*
         const float e2 = fabsf(den) >= kDenMin ? e : __int_as_float(0x7fc00000);
         asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(lo) : "f"(e2), "f"(tlo));
         asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(out) : "f"(e2), "f"(thi));
+    };
+    {   // four points per trip: the loads are issued together and the loop overhead is shared
+        int i = rg.i0 + slice;
+        for (; i + 3 * slices < i_end; i += 4 * slices) {
+            const float4 p0 = pts[i], p1 = pts[i + slices], p2 = pts[i + 2 * slices], p3 = pts[i + 3 * slices];
+            eval(p0); eval(p1); eval(p2); eval(p3);
+        }
+        for (; i < i_end; i += slices) eval(pts[i]);
     }
     if (live) { atomicAdd(&part[k], lo); atomicAdd(&part[kRsThreads + k], out); }
     __syncthreads();
     if (live && slice == 0) {
         int l = part[k], o = part[kRsThreads + k];
-        if (rg.mode == kSuffix) { l += lo_s[r0 + k]; o += hi_s[r0 + k]; }
+        if (rg.mode == kSuffix || rg.mode == kMid) { l += lo_s[r0 + k]; o += hi_s[r0 + k]; }
         lo_s[r0 + k] = static_cast<uint16_t>(l);
-        if (rg.mode == kPrefix) {
+        if (rg.mode == kPrefix || rg.mode == kMid) {
             hi_s[r0 + k] = static_cast<uint16_t>(o);
         } else {
             hi_s[r0 + k] = static_cast<uint16_t>(m - o);
@@ -483,14 +502,17 @@ __device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4*
 // remaining safe slots share their rows with the unsafe ones, never more thread-rows than a single region
 // would need), then the last partial row sliced over the matches.  With `prune`, batches and rows whose
 // hypotheses all lie behind the cut are skipped.
-__device__ __forceinline__ void score_slots(const FhArgs& a, const float4* pts, const uint16_t* vlist, uint16_t* lo_s,
+__device__ __forceinline__ void score_slots(const FhArgs& a, const float4* pts, const uint16_t* pos, const uint16_t* vlist, uint16_t* lo_s,
                                             uint16_t* hi_s, int* part_s, int* s_lbest, int* s_cut, int s_begin, int s_end,
                                             int n_safe, int m, float cmax, uint32_t pair_level, bool prune,
                                             bool first_row_alone, const PtRange rg) {
     const int tid = threadIdx.x;
     if (s_end <= s_begin) return;
     const int n_nochk = s_begin + max(0, min(n_safe, s_end) - s_begin) / kRsThreads * kRsThreads;
-    const int n_full = n_nochk + (s_end - n_nochk) / kRsThreads * kRsThreads;     // end of the last full row
+    int n_full = n_nochk + (s_end - n_nochk) / kRsThreads * kRsThreads;           // end of the last full row
+    // a tail of at least half a row joins the batched rows (its idle slots cost less than a one-hypothesis-per-thread
+    // pass over the matches); shorter tails are sliced over the matches below
+    if (s_end - n_full >= kRsThreads / 2) n_full = s_end;
 #pragma unroll 1
     for (int region = 0; region < 2; ++region) {
         const int r_begin = region ? n_nochk : s_begin, r_end = region ? n_full : n_nochk;
@@ -511,17 +533,17 @@ __device__ __forceinline__ void score_slots(const FhArgs& a, const float4* pts, 
             int my_lo;
             if (region == 0) {
                 switch (nj) {
-                    case 1:  my_lo = score_batch<1, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
-                    case 2:  my_lo = score_batch<2, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
-                    case 3:  my_lo = score_batch<3, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
-                    default: my_lo = score_batch<4, false>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    case 1:  my_lo = score_batch<1, false>(a, pts, pos, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    case 2:  my_lo = score_batch<2, false>(a, pts, pos, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    case 3:  my_lo = score_batch<3, false>(a, pts, pos, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    default: my_lo = score_batch<4, false>(a, pts, pos, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
                 }
             } else {
                 switch (nj) {
-                    case 1:  my_lo = score_batch<1, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
-                    case 2:  my_lo = score_batch<2, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
-                    case 3:  my_lo = score_batch<3, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
-                    default: my_lo = score_batch<4, true>(a, pts, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    case 1:  my_lo = score_batch<1, true>(a, pts, pos, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    case 2:  my_lo = score_batch<2, true>(a, pts, pos, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    case 3:  my_lo = score_batch<3, true>(a, pts, pos, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
+                    default: my_lo = score_batch<4, true>(a, pts, pos, vlist, lo_s, hi_s, s0, r_end, m, cmax, pair_level, s_cut, rg); break;
                 }
             }
             atomicMax(s_lbest, my_lo);
@@ -535,17 +557,19 @@ __device__ __forceinline__ void score_slots(const FhArgs& a, const float4* pts, 
                 alive = __syncthreads_or(slot < s_end && static_cast<int>(vlist[slot]) < *s_cut);
             }
             if (alive)
-                score_partial_row(a, pts, vlist, lo_s, hi_s, part_s, s_lbest, s_cut, n_full, s_end - n_full, m, cmax, pair_level, rg);
+                score_partial_row(a, pts, pos, vlist, lo_s, hi_s, part_s, s_lbest, s_cut, n_full, s_end - n_full, m, cmax, pair_level, rg);
         }
     }
 }
 
-// dynamic shared memory of the scoring kernel: float4 pts[max_cnt] | u16 vlist, slist, lo_s, hi_s [n_hyp] each
+// dynamic shared memory of the scoring kernel: float4 pts[max_cnt] | u16 pos[max_cnt (rounded up to 8)] |
+// u16 vlist, slist, lo_s, hi_s [n_hyp] each
 __global__ void __launch_bounds__(kRsThreads, 4)
 ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __restrict__ phase) {
     extern __shared__ __align__(16) uint8_t fh_smem[];
     float4* pts = reinterpret_cast<float4*>(fh_smem);
-    uint16_t* vlist = reinterpret_cast<uint16_t*>(fh_smem + static_cast<size_t>(a.max_cnt) * 16);   // valid hypotheses
+    uint16_t* pos = reinterpret_cast<uint16_t*>(fh_smem + static_cast<size_t>(a.max_cnt) * 16);      // sample index -> position in pts
+    uint16_t* vlist = pos + ((a.max_cnt + 7) & ~7);                                                   // valid hypotheses
     uint16_t* slist = vlist + a.n_hyp;                                                                // survivors to rescore
     uint16_t* lo_s = slist + a.n_hyp;                                                                 // count bounds per valid slot
     uint16_t* hi_s = lo_s + a.n_hyp;
@@ -553,7 +577,8 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     __shared__ float cmax_s[kRsThreads / 32];
     __shared__ int warp_sums[2 * (kRsThreads / 32)];
     __shared__ int part_s[2 * kRsThreads];
-    __shared__ int s_flag, s_nvalid, s_nsafe, s_nsurv, s_lbest, s_cut;
+    __shared__ float lead_s[10];
+    __shared__ int s_flag, s_nvalid, s_nsafe, s_nsurv, s_lbest, s_cut, s_leader;
 
     const int p = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -573,12 +598,13 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
             v = make_float4(pa.x, pa.y, pb.x, pb.y);
         }
         pts[i] = v;
+        pos[i] = static_cast<uint16_t>(i);
         cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
     }
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffff, cmax, of));
     if (lane == 0) cmax_s[warp] = cmax;
-    if (tid == 0) { s_nvalid = 0; s_nsurv = 0; s_lbest = 0; s_cut = 0x7FFFFFFF; }
+    if (tid == 0) { s_nvalid = 0; s_nsurv = 0; s_lbest = 0; s_cut = 0x7FFFFFFF; s_leader = 0x7FFFFFFF; }
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < kRsThreads / 32; ++w) cmax = fmaxf(cmax, cmax_s[w]);
@@ -609,7 +635,7 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     // ---------------- pass 0: which hypotheses pass the orientation / collinearity test (ordered compaction);
     // those with a provably safe denominator go first (vlist[0, n_safe)), the others after them
     const bool prune = a.exact_only == 0 && a.no_prune == 0;
-    bool probed = false;
+    int probed = 0;
     {
         int base = 0, base_u = 0;
         for (int h0 = 0; h0 < a.n_hyp; h0 += kRsThreads) {
@@ -618,7 +644,8 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
             if (hyp < a.n_hyp) {
                 int idx[4];
                 sample4(a.seed, pair_level, static_cast<uint32_t>(hyp), m, idx);
-                const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
+                float4 q[4];
+                load_sample(pts, pos, idx, q);
                 double H[9];
                 ok = solve4(q, H) ? 1 : 0;
                 safe = ok && den_safe(static_cast<float>(H[6]), static_cast<float>(H[7]), cmax);
@@ -640,12 +667,18 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
             base += total; base_u += total_u;
             __syncthreads();
             // Probe (level >= 2, where nearly every point is an inlier): as soon as the first chunk of
-            // hypotheses is classified, its kProbe lowest-index safe ones are scored, sliced over the matches
-            // like a partial row.  If one of them counts every match as a sure inlier, no hypothesis of a
-            // later chunk can win the (count desc, index asc) arg-max: they are not even sampled.
+            // hypotheses is classified, its lowest-index safe ones are scored, sliced over the matches like a
+            // partial row -- the first kProbe0, and when none of them counts every match as a sure inlier the rest
+            // of the first kProbe.  If one does, no hypothesis of a later chunk can win the (count desc, index asc)
+            // arg-max: they are not even sampled.
             if (prune && a.level >= 2 && h0 == 0 && base >= kProbe) {
-                score_partial_row(a, pts, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, 0, kProbe, m, cmax, pair_level, PtRange{0, m, kFull});
-                probed = true;
+                score_partial_row(a, pts, pos, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, 0, kProbe0, m, cmax, pair_level, PtRange{0, m, kFull});
+                probed = kProbe0;
+                if (s_cut == 0x7FFFFFFF) {
+                    score_partial_row(a, pts, pos, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, kProbe0, kProbe - kProbe0, m, cmax, pair_level,
+                                      PtRange{0, m, kFull});
+                    probed = kProbe;
+                }
                 if (s_cut != 0x7FFFFFFF) break;
             }
         }
@@ -657,70 +690,157 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
 
     // ---------------- pass 1: fused scoring of the valid hypotheses with count bounds [lo, hi]
     unsigned long long best_key = 0;      // (exact count << 32) | ~hyp   of hypotheses whose count is already exact
-    const int start = probed ? kProbe : 0;
+    const int start = probed;
     for (int slot = start + tid; slot < n_valid; slot += kRsThreads) { lo_s[slot] = 0; hi_s[slot] = 0; }   // skipped slots: hi = 0
     __syncthreads();
-    // Two-phase scoring at level 1 (exact): the first row is scored against every match, which gives a true
-    // lower bound lb on the winning count.  A hypothesis that collects more than m - lb sure outliers can no
-    // longer reach lb, so the other rows first see only the K0 = m - lb + margin leading matches (PREFIX);
-    // the hypotheses still in the race are compacted (order kept) and finish on the remaining matches
-    // (SUFFIX).  With 80 % inliers this retires every outlier-contaminated hypothesis after ~25 % of its work.
+    // Staged scoring at level 1 (exact).  A leading batch of kLead hypotheses is scored against every match (sliced
+    // over the matches like a partial row); its best sure-inlier count lb is a true lower bound on the winning
+    // count, so a hypothesis that has collected more than m - lb sure outliers can no longer win.  To make the
+    // others collect their outliers EARLY, the matches are partitioned in place by the leader (the leading
+    // hypothesis that reached lb): the m - lb matches it does not count as sure inliers first -- true outliers are
+    // outliers for every good hypothesis -- then the rest (pos[] keeps the sample indices valid).  The other
+    // hypotheses then run in stages over the matches; after every stage those with more than m - lb sure outliers,
+    // or behind the cut, are removed by an ordered compaction.  Outlier-contaminated hypotheses retire after the
+    // first stage (m - lb + 32 matches), good-but-worse ones a few stages later; only hypotheses as good as the
+    // leader see every match.  Counts do not depend on the order of the matches: results are identical to scoring
+    // everything (EVZ_OPT_RANSAC_NO_PRUNE).
     // (At level >= 2 the first row goes alone instead: the rows after it are usually pruned by the cut it finds.)
-    // One call site of score_slots in a small state machine keeps the kernel's code size down.
-    // (the batch that is scored against every match is only kLead hypotheses: sliced over the matches like a partial
-    // row it costs a quarter of a full row, and one all-inlier sample among 64 is as good as one among 256 for lb)
     const bool lead = prune && a.level == 1;
     const int s1 = start + (lead ? kLead : kRsThreads);
-    const bool two_phase = lead && n_valid > s1;
-    int lb = 0;
-    int sb = start, se = two_phase ? s1 : n_valid;
-    PtRange rg{0, m, kFull};
-    for (int state = 0; state < 3; ) {
-        score_slots(a, pts, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, sb, se, n_safe, m, cmax, pair_level, prune,
-                    state == 0 && prune && a.level >= 2, rg);
-        if (!two_phase || rg.mode == kSuffix || (state == 1 && rg.mode == kFull)) break;
+    const bool staged = lead && n_valid > s1;
+    if (!staged) {
+        score_slots(a, pts, pos, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, start, n_valid, n_safe, m, cmax, pair_level, prune,
+                    prune && a.level >= 2, PtRange{0, m, kFull});
+    } else {
+        score_slots(a, pts, pos, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, start, s1, n_safe, m, cmax, pair_level, prune, false,
+                    PtRange{0, m, kFull});
         __syncthreads();
-        if (state == 0) {
-            lb = s_lbest;
-            const int K0 = (m - lb + 48 + 31) & ~31;
-            sb = s1; se = n_valid;
-            if (lb >= 4 && K0 * 5 <= m * 3) rg = PtRange{0, K0, kPrefix};
-            state = 1;
-            continue;
-        }
-        // state 1, after the PREFIX pass: ordered in-place compaction of the hypotheses that can still reach lb
-        // (new position <= old position; every chunk is read, then written)
-        const int cutv = s_cut;
-        int base = s1, safe_alive = 0;
-        for (int c0 = s1; c0 < n_valid; c0 += kRsThreads) {
-            const int slot = c0 + tid;
-            int hyp = 0, l = 0, o = 0, alive = 0;
-            if (slot < n_valid) {
-                hyp = vlist[slot]; l = lo_s[slot]; o = hi_s[slot];
-                alive = (o <= m - lb && hyp < cutv) ? 1 : 0;
-            }
-            const unsigned bal = __ballot_sync(0xffffffff, alive);
-            const unsigned bal_sf = __ballot_sync(0xffffffff, alive && slot < n_safe);
-            if (lane == 0) { warp_sums[warp] = __popc(bal); warp_sums[kRsThreads / 32 + warp] = __popc(bal_sf); }
+        const int lb = s_lbest;
+        int b1 = m;                                    // end of the first stage
+        if (lb >= 4) {
+            // leader = lowest slot of the leading batch that reached lb; its model goes to shared memory
+            if (start + tid < s1 && lo_s[start + tid] == lb) atomicMin(&s_leader, start + tid);
             __syncthreads();
-            int before = 0, total = 0;
+            if (tid == 0) {
+                int idx[4];
+                sample4(a.seed, pair_level, static_cast<uint32_t>(vlist[s_leader]), m, idx);
+                float4 q[4];
+                load_sample(pts, pos, idx, q);
+                double H[9];
+                solve4(q, H);
+                float hf[8], tlo, thi;
+                for (int i = 0; i < 8; ++i) { hf[i] = static_cast<float>(H[i]); lead_s[i] = hf[i]; }
+                fused_thresholds(hf, cmax, a.thresh2, a.exact_only != 0, tlo, thi);
+                lead_s[8] = tlo;
+            }
+            __syncthreads();
+            float hl[8];
 #pragma unroll
-            for (int w = 0; w < kRsThreads / 32; ++w) {
-                const int c = warp_sums[w];
-                before += w < warp ? c : 0; total += c; safe_alive += warp_sums[kRsThreads / 32 + w];
+            for (int i = 0; i < 8; ++i) hl[i] = lead_s[i];
+            const float tlo_l = lead_s[8];
+            // class of a point: 1 = not a sure inlier of the leader (goes first).  Unordered in-place partition: the
+            // k-th misplaced "rest" point of the front region trades places with the k-th misplaced "first" point
+            // of the back region (lists of positions in slist / part_s).
+            int n_first = 0;
+            for (int c0 = 0; c0 < m; c0 += kRsThreads) {               // count the class-1 points
+                const int i = c0 + tid;
+                int f = 0;
+                if (i < m) {
+                    const float4 pt = pts[i];
+                    const float den = __fmaf_rn(hl[6], pt.x, __fmaf_rn(hl[7], pt.y, 1.f));
+                    const float e = reproj_err_fused(hl, pt);
+                    f = !(fabsf(den) >= kDenMin && e <= tlo_l);
+                }
+                n_first += __syncthreads_count(f);
             }
-            if (alive) {
-                const int d = base + before + __popc(bal & ((1u << lane) - 1u));
-                vlist[d] = static_cast<uint16_t>(hyp); lo_s[d] = static_cast<uint16_t>(l); hi_s[d] = static_cast<uint16_t>(o);
+            uint16_t* list_a = slist;                                      // misplaced class-0 points in [0, n_first)
+            uint16_t* list_b = reinterpret_cast<uint16_t*>(part_s);        // misplaced class-1 points in [n_first, m); <= 1024 entries
+            const int cap_b = static_cast<int>(sizeof(part_s) / sizeof(uint16_t));
+            int na = 0, nb = 0;
+            bool fits = true;
+            for (int c0 = 0; c0 < m; c0 += kRsThreads) {
+                const int i = c0 + tid;
+                int f = -1;
+                if (i < m) {
+                    const float4 pt = pts[i];
+                    const float den = __fmaf_rn(hl[6], pt.x, __fmaf_rn(hl[7], pt.y, 1.f));
+                    const float e = reproj_err_fused(hl, pt);
+                    f = !(fabsf(den) >= kDenMin && e <= tlo_l);
+                }
+                const int mis_a = i < m && i < n_first && f == 0, mis_b = i < m && i >= n_first && f == 1;
+                const unsigned bal_a = __ballot_sync(0xffffffff, mis_a), bal_b = __ballot_sync(0xffffffff, mis_b);
+                if (lane == 0) { warp_sums[warp] = __popc(bal_a); warp_sums[kRsThreads / 32 + warp] = __popc(bal_b); }
+                __syncthreads();
+                int before_a = 0, total_a = 0, before_b = 0, total_b = 0;
+#pragma unroll
+                for (int w = 0; w < kRsThreads / 32; ++w) {
+                    const int ca = warp_sums[w], cb = warp_sums[kRsThreads / 32 + w];
+                    before_a += w < warp ? ca : 0; total_a += ca;
+                    before_b += w < warp ? cb : 0; total_b += cb;
+                }
+                const unsigned below = (1u << lane) - 1u;
+                if (mis_a && na + before_a + __popc(bal_a & below) < a.n_hyp) list_a[na + before_a + __popc(bal_a & below)] = static_cast<uint16_t>(i);
+                if (mis_b && nb + before_b + __popc(bal_b & below) < cap_b) list_b[nb + before_b + __popc(bal_b & below)] = static_cast<uint16_t>(i);
+                na += total_a; nb += total_b;
+                __syncthreads();
             }
-            base += total;
+            fits = na <= a.n_hyp && nb <= cap_b;            // (na == nb always; the lists live in borrowed buffers)
+            if (fits) {
+                for (int k = tid; k < na; k += kRsThreads) {
+                    const int ia = list_a[k], ib = list_b[k];
+                    const float4 va = pts[ia], vb = pts[ib];
+                    pts[ia] = vb; pts[ib] = va;
+                    pos[ia] = static_cast<uint16_t>(ib); pos[ib] = static_cast<uint16_t>(ia);
+                }
+                b1 = min(m, (n_first + 32 + 31) & ~31);
+            }
             __syncthreads();
         }
-        n_safe = min(n_safe, s1) + safe_alive;
-        n_valid = base;
-        se = n_valid;
-        rg = PtRange{rg.i1, m, kSuffix};
-        state = 2;
+        // stages over the matches: [0, b1), then up to kStages - 1 equal parts of at least 128 matches
+        int n_rest_stages = b1 < m ? max(1, min(kStagesMax - 1, (m - b1) / 128)) : 0;
+        if (!(lb >= 4 && b1 * 5 <= m * 4)) { b1 = m; n_rest_stages = 0; }      // nothing to gain: one pass over everything
+        const int step = n_rest_stages ? ((m - b1 + n_rest_stages - 1) / n_rest_stages + 31) & ~31 : 0;
+        int i0 = 0, i1 = b1;
+        for (int stage = 0; ; ++stage) {
+            const bool last = i1 >= m;
+            const int mode = stage == 0 ? (last ? kFull : kPrefix) : (last ? kSuffix : kMid);
+            score_slots(a, pts, pos, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, s1, n_valid, n_safe, m, cmax, pair_level, prune, false,
+                        PtRange{i0, min(i1, m), mode});
+            if (last) break;
+            __syncthreads();
+            // ordered in-place compaction of the hypotheses that can still reach lb (new position <= old position;
+            // every chunk is read, then written)
+            const int cutv = s_cut;
+            int base = s1, safe_alive = 0;
+            for (int c0 = s1; c0 < n_valid; c0 += kRsThreads) {
+                const int slot = c0 + tid;
+                int hyp = 0, l = 0, ot = 0, alive = 0;
+                if (slot < n_valid) {
+                    hyp = vlist[slot]; l = lo_s[slot]; ot = hi_s[slot];
+                    alive = (ot <= m - lb && hyp < cutv) ? 1 : 0;
+                }
+                const unsigned bal = __ballot_sync(0xffffffff, alive);
+                const unsigned bal_sf = __ballot_sync(0xffffffff, alive && slot < n_safe);
+                if (lane == 0) { warp_sums[warp] = __popc(bal); warp_sums[kRsThreads / 32 + warp] = __popc(bal_sf); }
+                __syncthreads();
+                int before = 0, total = 0;
+#pragma unroll
+                for (int w = 0; w < kRsThreads / 32; ++w) {
+                    const int c = warp_sums[w];
+                    before += w < warp ? c : 0; total += c; safe_alive += warp_sums[kRsThreads / 32 + w];
+                }
+                if (alive) {
+                    const int d = base + before + __popc(bal & ((1u << lane) - 1u));
+                    vlist[d] = static_cast<uint16_t>(hyp); lo_s[d] = static_cast<uint16_t>(l); hi_s[d] = static_cast<uint16_t>(ot);
+                }
+                base += total;
+                __syncthreads();
+            }
+            n_safe = min(n_safe, s1) + safe_alive;
+            n_valid = base;
+            i0 = i1; i1 = min(m, i1 + step);
+            if (n_valid <= s1) break;                     // nobody left: the leading batch holds the winner
+        }
     }
     __syncthreads();
     const int lbest = s_lbest;
@@ -745,7 +865,8 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
         const int hyp = slist[k];
         int idx[4];
         sample4(a.seed, pair_level, static_cast<uint32_t>(hyp), m, idx);
-        const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
+        float4 q[4];
+        load_sample(pts, pos, idx, q);
         double H[9];
         solve4(q, H);
         float hf[8];
@@ -777,7 +898,8 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
         if (bc >= 4) {
             int idx[4];
             sample4(a.seed, pair_level, static_cast<uint32_t>(bh), m, idx);
-            const float4 q[4] = {pts[idx[0]], pts[idx[1]], pts[idx[2]], pts[idx[3]]};
+            float4 q[4];
+            load_sample(pts, pos, idx, q);
             double H[9];
             solve4(q, H);
             for (int i = 0; i < 9; ++i) Hbest_out[static_cast<size_t>(p) * 9 + i] = H[i];
@@ -954,7 +1076,7 @@ extern "C" int evz_find_homography(evz_handle* h, const float* pts, const int32_
     int32_t* phase = static_cast<int32_t*>(scr);
     double* hb = H_best ? H_best : reinterpret_cast<double*>(static_cast<uint8_t*>(scr) + ph_bytes);
     EVZ_REQUIRE(h, n_hyp <= 65535, "n_hyp must be below 65536");
-    const int smem_score = max_cnt * 16 + 8 * n_hyp + 16;
+    const int smem_score = max_cnt * 16 + ((max_cnt + 7) & ~7) * 2 + 8 * n_hyp + 16;
     const int smem_refit = max_cnt * 17 + 16;
     if (smem_score > h->attr_score) {
         EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::ransac_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_score));

@@ -102,3 +102,80 @@ def video_chain(frames, n_hyp=1024, seed=0, none_h_processing=True, reference_ex
             Hprev = H
         sup.append(np.eye(3) if S is None else np.asarray(S, np.float64))
     return dict(H_fixed=Hs, valid=valid, S=np.array(sup), status=status)
+
+
+def pair_static_multi(frames_q, frames_t, n_hyp=1024, seed=0, pair_id=0, ratio=0.5, thresh=3.0):
+    """`FrameProcessing.concatenate_all_features_types` (frame_processing.py:91-104) for one pair:
+    frames_q / frames_t are lists over feature types of (coords, desc) of the new / previous frame.
+    Every type goes through match_kps -> RANSAC #1 -> static filter (same pair_id and level 1 for
+    every type); the static points are concatenated in type order and de-duplicated.
+    Returns (status, static_a, static_b, per-type intermediates)."""
+    all_a, all_b, per = [], [], []
+    for (qc, qd), (tc, td) in zip(frames_q, frames_t):
+        if qd is None or td is None:
+            return ST_FEW_MATCHES, None, None, per         # matching.py:104-107: NoMatchesException
+        mk = matching.match_kps(qc, qd, tc, td, ratio)
+        if mk["status"] != 0:
+            return ST_FEW_MATCHES, None, None, per
+        r1 = ransac.find_homography_seeded(mk["pts_a"], mk["pts_b"], n_hyp, seed, pair_id, 1, thresh)
+        if r1["status"] != 0:
+            return (ST_FEW_POINTS if r1["status"] == ransac.ST_TOO_FEW else ST_NO_MODEL_1), None, None, per
+        keep, best_r, _ = static_filter.static_points(r1["H"], mk["pts_a"], mk["pts_b"])
+        per.append(dict(match=mk, ransac1=r1, keep=keep))
+        all_a.append(mk["pts_a"][keep]); all_b.append(mk["pts_b"][keep])
+    sa, sb, _, _ = matching.remove_double_matching(np.concatenate(all_a), np.concatenate(all_b))
+    return ST_OK, sa, sb, per
+
+
+def video_chain_multi(feats, n_hyp=1024, seed=0, none_h_processing=True, reference_exact=False,
+                      ratio=0.5, thresh=3.0):
+    """`get_homography_dict` (video_processing.py:67-105) over several feature types.
+    feats: {type: [(coords, desc) per frame]}.  Same return value as video_chain, plus the merged
+    static sets per pair (`static`)."""
+    types = list(feats)
+    F = len(feats[types[0]])
+    P = F - 1
+    status = np.zeros(P, np.int32)
+    static = []
+    G = np.tile(np.eye(3), (P, 1, 1))
+    valid = np.zeros(P, bool)
+    Hs, sup = [], [np.eye(3)]
+    S, Hprev, first = None, None, True
+    for p in range(P):
+        st, sa, sb, _ = pair_static_multi([feats[t][p + 1] for t in types], [feats[t][p] for t in types],
+                                          n_hyp, seed, p, ratio, thresh)
+        static.append((sa, sb))
+        H = None
+        if st == ST_OK:
+            if reference_exact and S is not None:
+                Sp = np.asarray(S, np.float64)
+                sa2 = np.array([chain.homography_transformation(q, Sp) for q in sa]).reshape(-1, 2)
+                sb2 = np.array([chain.homography_transformation(q, Sp) for q in sb]).reshape(-1, 2)
+            else:
+                sa2, sb2 = sa, sb
+            r2 = ransac.find_homography_seeded(sa2, sb2, n_hyp, seed, p, 2, thresh)
+            if r2["status"] != 0:
+                st = ST_FEW_POINTS if r2["status"] == ransac.ST_TOO_FEW else ST_NO_MODEL_2
+            elif int(r2["mask"].sum()) < LENGTH_ACCOUNTED_POINTS * len(r2["mask"]):
+                st = ST_FEW_INLIERS
+            else:
+                H = r2["H"]
+        status[p] = st
+        valid[p] = H is not None
+        if not reference_exact:
+            if H is not None:
+                G[p] = H
+            continue
+        if H is None:
+            H = Hprev if none_h_processing else None
+        Hs.append(H)
+        S = chain.matrix_superposition(H, S, first) if H is not None or S is not None else S
+        if H is not None:
+            first = False
+            Hprev = H
+        sup.append(np.eye(3) if S is None else np.asarray(S, np.float64))
+    if not reference_exact:
+        Gf = chain.fill_none(G, valid, none_h_processing)
+        Sx = chain.chain_products(Gf)
+        return dict(G=G, valid=valid, S=Sx, status=status, H_fixed=chain.fixed_plane_H(Sx), static=static)
+    return dict(H_fixed=Hs, valid=valid, S=np.array(sup), status=status, static=static)

@@ -29,10 +29,10 @@ namespace evz {
 constexpr int kRsThreads = 256;   // scoring kernel
 constexpr int kRfThreads = 64;    // refit kernel
 constexpr int kHpt = 4;           // hypotheses scored concurrently per thread
-constexpr int kProbe = 64;        // hypotheses of the level-2 probe (see ransac_score_kernel)
-constexpr int kProbe0 = 16;       // ... of which this many go first
+constexpr int kGrp = 32;          // hypotheses per group of the level-2 search (first_perfect_search)
 constexpr int kStagesMax = 6;     // stages of the level-1 staged scoring
 constexpr int kLmMaxIters = 20;   // OpenCV uses 10 from a DLT start; we start from the 4-point model
+constexpr double kPxTol = 1e-6;   // LM stops when a step moves every point by less than this many pixels
 constexpr int kNSums = 32;        // 21 JtJ + 8 Jtr + S + max|r| (+1 pad)
 
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
@@ -242,6 +242,7 @@ struct LmShared {
     double S, lam, lc;
     double sums[kNSums];
     double wsum[kRfThreads / 32][kNSums];
+    float cmax_w[kRfThreads / 32];
     int iter, go;
 };
 
@@ -562,6 +563,79 @@ __device__ __forceinline__ void score_slots(const FhArgs& a, const float4* pts, 
     }
 }
 
+// Level >= 2 (static points: nearly every point is an inlier of nearly every hypothesis).  The arg-max is
+// (count desc, index asc), and no count exceeds m: the winner is the LOWEST-INDEX hypothesis that counts every point,
+// if there is one.  Hypotheses are therefore examined in index order, kGrp at a time (thread = hypothesis x slice of
+// the points, the model solved once per hypothesis and shared through shared memory), and a hypothesis is dropped at
+// its first SURE outlier -- it cannot reach m.  The search stops at the first group that holds a hypothesis with m sure
+// inliers (its index goes to *cut).  Candidates = that hypothesis and every earlier one without a sure outlier
+// (unsure evaluations only): they are appended to slist and counted exactly by the rescoring pass.  Returns false
+// when no hypothesis counts every point as a sure inlier: the caller then scores everything the general way.
+__device__ __forceinline__ bool first_perfect_search(const FhArgs& a, const float4* pts, const uint16_t* pos, uint16_t* slist, int* part,
+                                                     float* grp, int* dead, int* n_surv, int* cut, int m, float cmax,
+                                                     uint32_t pair_level) {
+    const int tid = threadIdx.x;
+    constexpr int kSlices = kRsThreads / kGrp;
+    const int k = tid & (kGrp - 1), slice = tid / kGrp;
+    for (int g0 = 0; g0 < a.n_hyp; g0 += kGrp) {
+        if (tid < kGrp) {
+            const int hyp = g0 + tid;
+            int ok = 0;
+            if (hyp < a.n_hyp) {
+                int idx[4];
+                sample4(a.seed, pair_level, static_cast<uint32_t>(hyp), m, idx);
+                float4 q[4];
+                load_sample(pts, pos, idx, q);
+                double H[9];
+                ok = solve4(q, H) ? 1 : 0;
+                float hf[8], tlo, thi;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { hf[i] = static_cast<float>(H[i]); grp[tid * 10 + i] = hf[i]; }
+                fused_thresholds(hf, cmax, a.thresh2, false, tlo, thi);
+                grp[tid * 10 + 8] = tlo; grp[tid * 10 + 9] = thi;
+            }
+            dead[tid] = ok ? 0 : 1;
+            part[tid] = 0;
+        }
+        __syncthreads();
+        float hf[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hf[i] = grp[k * 10 + i];
+        const float tlo = grp[k * 10 + 8], thi = grp[k * 10 + 9];
+        volatile int* vdead = dead;
+        int lo = 0;
+        for (int i = slice; i < m && !vdead[k]; i += 4 * kSlices) {
+            int outl = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ii = i + u * kSlices;
+                if (ii < m) {
+                    const float4 pt = pts[ii];
+                    const float den = __fmaf_rn(hf[6], pt.x, __fmaf_rn(hf[7], pt.y, 1.f));
+                    const float e = reproj_err_fused(hf, pt);
+                    const bool cls = fabsf(den) >= kDenMin;
+                    lo += (cls && e <= tlo) ? 1 : 0;
+                    outl |= (cls && e >= thi) ? 1 : 0;
+                }
+            }
+            if (outl) vdead[k] = 1;
+        }
+        if (lo) atomicAdd(&part[k], lo);
+        __syncthreads();
+        if (tid < kGrp && g0 + tid < a.n_hyp && !dead[tid]) {
+            if (part[tid] == m) atomicMin(cut, g0 + tid);
+            slist[atomicAdd(n_surv, 1)] = static_cast<uint16_t>(g0 + tid);
+        }
+        __syncthreads();
+        if (*cut != 0x7FFFFFFF) return true;
+    }
+    __syncthreads();
+    if (tid == 0) *n_surv = 0;               // no perfect hypothesis: the general path starts from scratch
+    __syncthreads();
+    return false;
+}
+
+
 // dynamic shared memory of the scoring kernel: float4 pts[max_cnt] | u16 pos[max_cnt (rounded up to 8)] |
 // u16 vlist, slist, lo_s, hi_s [n_hyp] each
 __global__ void __launch_bounds__(kRsThreads, 4)
@@ -578,6 +652,8 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     __shared__ int warp_sums[2 * (kRsThreads / 32)];
     __shared__ int part_s[2 * kRsThreads];
     __shared__ float lead_s[10];
+    __shared__ float grp_s[kGrp * 10];
+    __shared__ int grp_dead[kGrp];
     __shared__ int s_flag, s_nvalid, s_nsafe, s_nsurv, s_lbest, s_cut, s_leader;
 
     const int p = blockIdx.x;
@@ -635,8 +711,10 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     // ---------------- pass 0: which hypotheses pass the orientation / collinearity test (ordered compaction);
     // those with a provably safe denominator go first (vlist[0, n_safe)), the others after them
     const bool prune = a.exact_only == 0 && a.no_prune == 0;
-    int probed = 0;
-    {
+    bool found = false;
+    if (prune && a.level >= 2)
+        found = first_perfect_search(a, pts, pos, slist, part_s, grp_s, grp_dead, &s_nsurv, &s_cut, m, cmax, pair_level);
+    if (!found) {
         int base = 0, base_u = 0;
         for (int h0 = 0; h0 < a.n_hyp; h0 += kRsThreads) {
             const int hyp = h0 + tid;
@@ -666,31 +744,16 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
             else if (ok) slist[base_u + before_u + __popc(bal_u & below)] = static_cast<uint16_t>(hyp);
             base += total; base_u += total_u;
             __syncthreads();
-            // Probe (level >= 2, where nearly every point is an inlier): as soon as the first chunk of
-            // hypotheses is classified, its lowest-index safe ones are scored, sliced over the matches like a
-            // partial row -- the first kProbe0, and when none of them counts every match as a sure inlier the rest
-            // of the first kProbe.  If one does, no hypothesis of a later chunk can win the (count desc, index asc)
-            // arg-max: they are not even sampled.
-            if (prune && a.level >= 2 && h0 == 0 && base >= kProbe) {
-                score_partial_row(a, pts, pos, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, 0, kProbe0, m, cmax, pair_level, PtRange{0, m, kFull});
-                probed = kProbe0;
-                if (s_cut == 0x7FFFFFFF) {
-                    score_partial_row(a, pts, pos, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, kProbe0, kProbe - kProbe0, m, cmax, pair_level,
-                                      PtRange{0, m, kFull});
-                    probed = kProbe;
-                }
-                if (s_cut != 0x7FFFFFFF) break;
-            }
         }
         for (int k = tid; k < base_u; k += kRsThreads) vlist[base + k] = slist[k];
         if (tid == 0) { s_nvalid = base + base_u; s_nsafe = base; }
     }
     __syncthreads();
-    int n_valid = s_nvalid, n_safe = s_nsafe;
+    int n_valid = found ? 0 : s_nvalid, n_safe = found ? 0 : s_nsafe;
 
     // ---------------- pass 1: fused scoring of the valid hypotheses with count bounds [lo, hi]
     unsigned long long best_key = 0;      // (exact count << 32) | ~hyp   of hypotheses whose count is already exact
-    const int start = probed;
+    const int start = 0;
     for (int slot = start + tid; slot < n_valid; slot += kRsThreads) { lo_s[slot] = 0; hi_s[slot] = 0; }   // skipped slots: hi = 0
     __syncthreads();
     // Staged scoring at level 1 (exact).  A leading batch of kLead hypotheses is scored against every match (sliced
@@ -708,7 +771,9 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     const bool lead = prune && a.level == 1;
     const int s1 = start + (lead ? kLead : kRsThreads);
     const bool staged = lead && n_valid > s1;
-    if (!staged) {
+    if (found) {
+        // level >= 2: the candidates are already in slist
+    } else if (!staged) {
         score_slots(a, pts, pos, vlist, lo_s, hi_s, part_s, &s_lbest, &s_cut, start, n_valid, n_safe, m, cmax, pair_level, prune,
                     prune && a.level >= 2, PtRange{0, m, kFull});
     } else {
@@ -717,6 +782,7 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
         __syncthreads();
         const int lb = s_lbest;
         int b1 = m;                                    // end of the first stage
+        int leader_hyp = 0x7FFFFFFF;
         if (lb >= 4) {
             // leader = lowest slot of the leading batch that reached lb; its model goes to shared memory
             if (start + tid < s1 && lo_s[start + tid] == lb) atomicMin(&s_leader, start + tid);
@@ -734,6 +800,7 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
                 lead_s[8] = tlo;
             }
             __syncthreads();
+            leader_hyp = vlist[s_leader];
             float hl[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) hl[i] = lead_s[i];
@@ -817,7 +884,8 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
                 int hyp = 0, l = 0, ot = 0, alive = 0;
                 if (slot < n_valid) {
                     hyp = vlist[slot]; l = lo_s[slot]; ot = hi_s[slot];
-                    alive = (ot <= m - lb && hyp < cutv) ? 1 : 0;
+                    // (count desc, index asc): behind the leader a hypothesis needs strictly more than lb inliers
+                    alive = (ot <= m - lb - (hyp > leader_hyp ? 1 : 0) && hyp < cutv) ? 1 : 0;
                 }
                 const unsigned bal = __ballot_sync(0xffffffff, alive);
                 const unsigned bal_sf = __ballot_sync(0xffffffff, alive && slot < n_safe);
@@ -924,6 +992,7 @@ ransac_refit_kernel(const FhArgs a, const double* __restrict__ Hbest_in, const i
     const int64_t o = a.off[p];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* T = a.pre_H ? a.pre_H + static_cast<size_t>(p) * 9 : nullptr;
+    float cmax = 0.f;
     for (int i = tid; i < m; i += blockDim.x) {
         float4 v = reinterpret_cast<const float4*>(a.pts)[o + i];
         if (T) {
@@ -931,9 +1000,16 @@ ransac_refit_kernel(const FhArgs a, const double* __restrict__ Hbest_in, const i
             v = make_float4(pa.x, pa.y, pb.x, pb.y);
         }
         pts[i] = v;
+        cmax = fmaxf(cmax, fmaxf(fabsf(v.x), fabsf(v.y)));
     }
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffff, cmax, of));
+    if (lane == 0) L.cmax_w[warp] = cmax;
     if (tid < 8) L.x[tid] = Hbest_in[static_cast<size_t>(p) * 9 + tid];
     __syncthreads();
+#pragma unroll
+    for (int w = 0; w < kRfThreads / 32; ++w) cmax = fmaxf(cmax, L.cmax_w[w]);
+    const double cm = static_cast<double>(fmaxf(cmax, 1.f));
 
     // ---------------- phase 3: winner's inlier mask, then LM refit on it
     {
@@ -952,7 +1028,9 @@ ransac_refit_kernel(const FhArgs a, const double* __restrict__ Hbest_in, const i
         lm_expand(L.sums, L.A, L.v);
         for (int i = 0; i < 8; ++i) L.D[i] = L.A[i * 8 + i];
         L.S = L.sums[29];
-        L.lam = 1.0; L.lc = 0.75; L.iter = 0;
+        // (OpenCV starts at lambda = 1 from a DLT estimate; from the winning 4-point model an undamped first step saves
+        // one pass over the inliers and reaches the same optimum -- a step that does not reduce S is damped as usual)
+        L.lam = 0.0; L.lc = 0.75; L.iter = 0;
         L.go = L.sums[30] >= static_cast<double>(FLT_EPSILON);
     }
     __syncthreads();
@@ -968,6 +1046,11 @@ ransac_refit_kernel(const FhArgs a, const double* __restrict__ Hbest_in, const i
             ldl8_solve(f, vv, d);
 #pragma unroll
             for (int i = 0; i < 8; ++i) { if (!f.ok) d[i] = 0.0; xd[i] = L.x[i] - d[i]; }
+            // a step that moves no point of the data range by more than kPxTol pixels is not worth a pass over the
+            // inliers: converged (every thread holds the same d, so the exit is uniform)
+            const double px = fmax(fmax(fabs(d[0]), fabs(d[1])), fmax(fabs(d[3]), fabs(d[4]))) * cm + fmax(fabs(d[2]), fabs(d[5])) +
+                              fmax(fabs(d[6]), fabs(d[7])) * cm * cm;
+            if (f.ok && px < kPxTol) break;
         }
         lm_accumulate(xd, pts, msk, m, L);
         if (tid == 0) {

@@ -254,7 +254,7 @@ def run_ours(args, cfg):
         r = eng.match(st, pq, pt)
         if timed: e[1].record()
         h1 = eng.find_homography(r.m_pts, r.out_off, r.m_cnt, r.status, N, n_hyp, 0, pair_base, 1, 3.0, 0.0, 4)
-        sp, sc, sr, fl = eng.static_filter(r.m_pts, r.out_off, r.m_cnt, h1["H"], r.status)
+        sp, sc, sr, fl = eng.static_filter(r.m_pts, r.out_off, r.m_cnt, h1["H"], r.status, max_cnt=N)
         h2 = eng.find_homography(sp, r.out_off, sc, r.status, N, n_hyp, 0, pair_base, 2, 3.0, 0.7, 5)
         if timed: e[2].record()
         if world > 1:

@@ -44,7 +44,10 @@ static_filter_kernel(const float* __restrict__ pts, const int32_t* __restrict__ 
     const int p = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (status[p] != EVZ_ST_OK) { if (tid == 0) { out_cnt[p] = 0; best_r[p] = -1; flags[p] = 0; } return; }
-    const int m = min(cnt[p], EVZ_MAX_KP);       // the frame store never holds more per frame (memory safety only)
+    // the host entry point refuses max_cnt > EVZ_MAX_KP; a pair that exceeds it anyway (the caller's bound was wrong)
+    // is reported, not truncated
+    if (cnt[p] > EVZ_MAX_KP) { if (tid == 0) { out_cnt[p] = 0; best_r[p] = -1; flags[p] = EVZ_FLAG_TOO_MANY_POINTS; } return; }
+    const int m = cnt[p];
     const int64_t o = off[p];
     double H[9];
 #pragma unroll
@@ -349,11 +352,15 @@ __global__ void max_reduce_kernel(const double* __restrict__ partial, int n, dou
 }  // namespace evz
 
 extern "C" int evz_static_filter(evz_handle* h, const float* pts, const int32_t* off, const int32_t* cnt, int n_pairs,
-                                 const double* H, const int32_t* status,
+                                 int max_cnt, const double* H, const int32_t* status,
                                  float* out_pts, int32_t* out_cnt, int32_t* best_r, int32_t* flags, int32_t* r_out,
                                  void* stream) {
     if (!h) return EVZ_E_ARG;
     EVZ_REQUIRE(h, pts && off && cnt && H && status && out_pts && out_cnt && best_r && flags, "null pointer");
+    if (max_cnt > EVZ_MAX_KP) {
+        EVZ_SET_ERR(h, "evz_static_filter: max_cnt %d exceeds the supported %d points per pair", max_cnt, EVZ_MAX_KP);
+        return EVZ_E_UNSUPPORTED;
+    }
     if (n_pairs <= 0) return EVZ_OK;
     const int smem = EVZ_MAX_KP * 2 + evz::kSfWindow * 8;
     if (!h->attr_static) {

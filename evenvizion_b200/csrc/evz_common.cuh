@@ -27,7 +27,7 @@ struct evz_handle {
     evz_encode_tiled_fn encode = nullptr;
     // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remembered per handle, not per process
     unsigned attr_match = 0;       // bit per match kernel instance
-    bool attr_static = false, attr_canon = false;
+    bool attr_static = false, attr_canon = false, attr_concat = false;
     int attr_filter = 0, attr_score = 0, attr_refit = 0;
     // options (evz_set_option)
     int opt_ransac_exact = 0;

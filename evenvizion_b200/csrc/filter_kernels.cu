@@ -221,6 +221,86 @@ filter_matches_kernel(const FilterArgs a) {
     }
 }
 
+// K5b: concatenate + de-duplicate the static points of several feature types, one CTA per pair.  Shared-memory
+// open-addressing table over the a-point coordinates: first[s] / last[s] = smallest / largest element index with the
+// key that owns slot s (element = position in the concatenation over the types).
+struct ConcatArgs {
+    const float* pts[EVZ_MAX_TYPES]; const int32_t* off[EVZ_MAX_TYPES]; const int32_t* cnt[EVZ_MAX_TYPES];
+    int n_types;
+    const int32_t* status; const int32_t* out_off; float* out_pts; int32_t* out_cnt;
+};
+constexpr int kConcatTable = 16384;          // slots: load factor <= 0.75 at EVZ_MAX_KP elements
+
+__global__ void __launch_bounds__(256)
+concat_dedup_kernel(const ConcatArgs a) {
+    extern __shared__ int32_t csm[];
+    __shared__ int warp_sums[32];
+    int32_t* first = csm;
+    int32_t* last = csm + kConcatTable;
+    const int p = blockIdx.x;
+    int base_t[EVZ_MAX_TYPES + 1];
+    base_t[0] = 0;
+#pragma unroll
+    for (int t = 0; t < EVZ_MAX_TYPES; ++t) base_t[t + 1] = base_t[t] + (t < a.n_types ? a.cnt[t][p] : 0);
+    const int total = base_t[EVZ_MAX_TYPES];
+    if (a.status[p] != EVZ_ST_OK || total <= 0 || total > EVZ_MAX_KP) { if (threadIdx.x == 0) a.out_cnt[p] = 0; return; }
+    auto elem = [&](int e) -> float4 {
+        int t = 0;
+#pragma unroll
+        for (int u = 1; u < EVZ_MAX_TYPES; ++u) t += (u < a.n_types && e >= base_t[u]) ? 1 : 0;
+        return reinterpret_cast<const float4*>(a.pts[t])[static_cast<int64_t>(a.off[t][p]) + (e - base_t[t])];
+    };
+    int cap = 64;
+    while (cap < total + total / 3 + 1 && cap < kConcatTable) cap <<= 1;
+    const unsigned int mask = cap - 1;
+    for (int i = threadIdx.x; i < cap; i += blockDim.x) { first[i] = -1; last[i] = -1; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const float4 v = elem(e);
+        const unsigned long long key = coord_key(v.x, v.y);
+        unsigned int s = hash64(key) & mask;
+        while (true) {
+            int cur = first[s];
+            if (cur < 0) {
+                cur = atomicCAS(&first[s], -1, e);
+                if (cur < 0) { atomicMax(&last[s], e); break; }
+            }
+            const float4 c = elem(cur);
+            if (coord_key(c.x, c.y) == key) { atomicMin(&first[s], e); atomicMax(&last[s], e); break; }
+            s = (s + 1) & mask;
+        }
+    }
+    __syncthreads();
+    const int64_t o0 = a.out_off[p];
+    int base = 0;
+    for (int eb = 0; eb < total; eb += blockDim.x) {
+        const int e = eb + threadIdx.x;
+        int emit = 0, l = 0;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < total) {
+            v = elem(e);
+            const unsigned long long key = coord_key(v.x, v.y);
+            unsigned int s = hash64(key) & mask;
+            while (true) {
+                const float4 c = elem(first[s]);
+                if (coord_key(c.x, c.y) == key) break;
+                s = (s + 1) & mask;
+            }
+            emit = first[s] == e;
+            l = last[s];
+        }
+        int tot;
+        const int pos = base + block_excl_scan(emit, warp_sums, tot);
+        if (emit) {
+            const float4 w = elem(l);
+            reinterpret_cast<float4*>(a.out_pts)[o0 + pos] = make_float4(v.x, v.y, w.z, w.w);
+        }
+        base += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.out_cnt[p] = base;
+}
+
 }  // namespace evz
 
 extern "C" int evz_ingest(evz_handle* h, const void* raw_desc, int raw_is_f32, int d,
@@ -268,6 +348,33 @@ extern "C" int evz_filter_matches(evz_handle* h, const int32_t* top2_idx, const 
     evz::FilterArgs a{top2_idx, top2_d2, coords, canon, row_off, n_kp, pair_q, pair_t, out_off, ratio, min_matching_pts,
                       surv, m_idx, m_pts, m_cnt, n_filtered, status};
     evz::filter_matches_kernel<<<n_pairs, 512, smem, st>>>(a);
+    EVZ_LAUNCH_CHECK(h);
+    return EVZ_OK;
+}
+
+extern "C" int evz_concat_dedup(evz_handle* h, int n_types, const float* const* pts, const int32_t* const* off, const int32_t* const* cnt,
+                                int n_pairs, const int32_t* status, int max_total, const int32_t* out_off,
+                                float* out_pts, int32_t* out_cnt, void* stream) {
+    if (!h) return EVZ_E_ARG;
+    EVZ_REQUIRE(h, n_types >= 1 && n_types <= EVZ_MAX_TYPES, "n_types must be in [1, EVZ_MAX_TYPES]");
+    EVZ_REQUIRE(h, pts && off && cnt && status && out_off && out_pts && out_cnt, "null pointer");
+    if (max_total > EVZ_MAX_KP) {
+        EVZ_SET_ERR(h, "evz_concat_dedup: max_total %d exceeds the supported %d points per pair", max_total, EVZ_MAX_KP);
+        return EVZ_E_UNSUPPORTED;
+    }
+    if (n_pairs <= 0) return EVZ_OK;
+    evz::ConcatArgs a{};
+    for (int t = 0; t < n_types; ++t) {
+        EVZ_REQUIRE(h, pts[t] && off[t] && cnt[t], "null pointer");
+        a.pts[t] = pts[t]; a.off[t] = off[t]; a.cnt[t] = cnt[t];
+    }
+    a.n_types = n_types; a.status = status; a.out_off = out_off; a.out_pts = out_pts; a.out_cnt = out_cnt;
+    const int smem = evz::kConcatTable * 8;
+    if (!h->attr_concat) {
+        EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::concat_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        h->attr_concat = true;
+    }
+    evz::concat_dedup_kernel<<<n_pairs, 256, smem, static_cast<cudaStream_t>(stream)>>>(a);
     EVZ_LAUNCH_CHECK(h);
     return EVZ_OK;
 }

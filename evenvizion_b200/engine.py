@@ -220,18 +220,19 @@ class GeometryEngine:
 
     # ------------------------------------------------------------------ K3 / K4
     def find_homography(self, pts, off, cnt, status, max_cnt, n_hyp=1024, seed=0, pair_id_base=0, level=1,
-                        thresh=3.0, min_inlier_frac=0.0, fail_status=_lib.ST_NO_MODEL_1, pre_H=None):
+                        thresh=3.0, min_inlier_frac=0.0, fail_status=_lib.ST_NO_MODEL_1, pre_H=None, light=False):
         """Batched seeded RANSAC + LM refit over the point lists pts[off[p]:off[p]+cnt[p]].
-        status is updated in place.  Returns dict(H, mask, inl_cnt, best_hyp, best_cnt, mask_best, H_best)."""
+        status is updated in place.  Returns dict(H, mask, inl_cnt, best_hyp, best_cnt, mask_best, H_best);
+        light=True skips the per-point masks and the diagnostics (H and inl_cnt only)."""
         P = int(cnt.numel())
         rows = int(pts.shape[0])
-        out = dict(H=torch.zeros((P, 9), dtype=torch.float64, device=self.device),
-                   mask=torch.zeros((rows,), dtype=torch.uint8, device=self.device),
-                   inl_cnt=torch.zeros((P,), dtype=torch.int32, device=self.device),
-                   best_hyp=torch.full((P,), -1, dtype=torch.int32, device=self.device),
-                   best_cnt=torch.zeros((P,), dtype=torch.int32, device=self.device),
-                   mask_best=torch.zeros((rows,), dtype=torch.uint8, device=self.device),
-                   H_best=torch.zeros((P, 9), dtype=torch.float64, device=self.device))
+        z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=self.device)
+        out = dict(H=z((P, 9), torch.float64), inl_cnt=z((P,), torch.int32))
+        if light:
+            out.update(mask=None, best_hyp=None, best_cnt=None, mask_best=None, H_best=None)
+        else:
+            out.update(mask=z((rows,), torch.uint8), best_hyp=torch.full((P,), -1, dtype=torch.int32, device=self.device),
+                       best_cnt=z((P,), torch.int32), mask_best=z((rows,), torch.uint8), H_best=z((P, 9), torch.float64))
         self._check(self.lib.evz_find_homography(self.h, _ptr(pts), _ptr(off), _ptr(cnt), P, int(max_cnt), _ptr(pre_H),
                                                  int(n_hyp), int(seed) & 0xFFFFFFFF, int(pair_id_base), int(level),
                                                  float(thresh), float(min_inlier_frac), int(fail_status),
@@ -241,19 +242,37 @@ class GeometryEngine:
         return out
 
     # ------------------------------------------------------------------ K5
-    def static_filter(self, pts, off, cnt, H, status, want_r=False):
+    def static_filter(self, pts, off, cnt, H, status, want_r=False, max_cnt=None):
+        """K5.  max_cnt: host-known upper bound of cnt (read back from the device when omitted)."""
         P = int(cnt.numel())
+        if max_cnt is None:
+            max_cnt = int(cnt.max().item()) if P else 0
         r_out = self._empty((int(pts.shape[0]),), torch.int32) if want_r else None
         out_pts = self._empty(tuple(pts.shape), torch.float32)
         out_cnt = self._empty((P,), torch.int32)
         best_r = self._empty((P,), torch.int32)
         flags = self._empty((P,), torch.int32)
-        self._check(self.lib.evz_static_filter(self.h, _ptr(pts), _ptr(off), _ptr(cnt), P, _ptr(H), _ptr(status),
+        self._check(self.lib.evz_static_filter(self.h, _ptr(pts), _ptr(off), _ptr(cnt), P, int(max_cnt), _ptr(H), _ptr(status),
                                                _ptr(out_pts), _ptr(out_cnt), _ptr(best_r), _ptr(flags), _ptr(r_out),
                                                self._stream()))
         if want_r:
             return out_pts, out_cnt, best_r, flags, r_out
         return out_pts, out_cnt, best_r, flags
+
+    def concat_dedup(self, parts, status, out_off, out_rows, max_total):
+        """K5b: per-pair concatenation of the point lists `parts` = [(pts, off, cnt), ...] (one entry per feature type)
+        followed by remove_double_matching.  Returns (out_pts [out_rows, 4], out_cnt [P])."""
+        n = len(parts)
+        P = int(status.numel())
+        arr = C.c_void_p * n
+        pts = arr(*[p[0].data_ptr() for p in parts])
+        off = arr(*[p[1].data_ptr() for p in parts])
+        cnt = arr(*[p[2].data_ptr() for p in parts])
+        out_pts = self._empty((int(out_rows), 4), torch.float32)
+        out_cnt = self._empty((P,), torch.int32)
+        self._check(self.lib.evz_concat_dedup(self.h, n, pts, off, cnt, P, _ptr(status), int(max_total), _ptr(out_off),
+                                              _ptr(out_pts), _ptr(out_cnt), self._stream()))
+        return out_pts, out_cnt
 
     # ------------------------------------------------------------------ whole per-pair path
     def process_pairs(self, st: FrameStore, pair_q, pair_t, n_hyp=1024, seed=0, pair_id_base=0,
@@ -267,7 +286,7 @@ class GeometryEngine:
         r.H1, r.mask1, r.mask1_best, r.best_hyp1, r.best_cnt1, r.inl1 = (h1["H"], h1["mask"], h1["mask_best"],
                                                                       h1["best_hyp"], h1["best_cnt"], h1["inl_cnt"])
         r.extra["H1_best"] = h1["H_best"]
-        r.static_pts, r.static_cnt, r.static_r, r.flags = self.static_filter(r.m_pts, r.out_off, r.m_cnt, r.H1, r.status)
+        r.static_pts, r.static_cnt, r.static_r, r.flags = self.static_filter(r.m_pts, r.out_off, r.m_cnt, r.H1, r.status, max_cnt=mk)
         h2 = self.find_homography(r.static_pts, r.out_off, r.static_cnt, r.status, mk, n_hyp, seed, pair_id_base, 2,
                                   thresh, 0.7, _lib.ST_NO_MODEL_2, pre_H=pre_H)
         r.H, r.mask2, r.mask2_best, r.best_hyp2, r.best_cnt2, r.inl2 = (h2["H"], h2["mask"], h2["mask_best"],
@@ -325,7 +344,7 @@ class GeometryEngine:
                                             int(seed) & 0xFFFFFFFF, int(pair_id_base) + p0, 1, float(thresh), 0.0,
                                             _lib.ST_NO_MODEL_1, at(r.status), at(r.H1, 9), _ptr(r.mask1), at(r.inl1),
                                             at(r.best_hyp1), at(r.best_cnt1), _ptr(r.mask1_best), at(r.extra["H1_best"], 9), strm))
-        self._check(lib.evz_static_filter(h, _ptr(r.m_pts), at(r.out_off), at(r.m_cnt), n, at(r.H1, 9), at(r.status),
+        self._check(lib.evz_static_filter(h, _ptr(r.m_pts), at(r.out_off), at(r.m_cnt), n, mk, at(r.H1, 9), at(r.status),
                                           _ptr(r.static_pts), at(r.static_cnt), at(r.static_r), at(r.flags), None, strm))
         self._check(lib.evz_find_homography(h, _ptr(r.static_pts), at(r.out_off), at(r.static_cnt), n, mk, None, int(n_hyp),
                                             int(seed) & 0xFFFFFFFF, int(pair_id_base) + p0, 2, float(thresh), 0.7,

@@ -87,7 +87,7 @@ class KeyPoints:
             raise NoMatchesException("fewer than 4 matching points after de-duplication", "couldn't process")
         if s != 0:
             raise NoMatchesException("can't find homography matrix", "couldn't process")
-        sp, sc, _, _ = eng.static_filter(r.m_pts, r.out_off, r.m_cnt, h1["H"], r.status)
+        sp, sc, _, _ = eng.static_filter(r.m_pts, r.out_off, r.m_cnt, h1["H"], r.status, max_cnt=st.max_kp)
         o, m = int(st.row_off_h[1]), int(sc[0])
         pts = sp[o:o + m].cpu().numpy()
         return pts[:, :2].copy(), pts[:, 2:].copy()

@@ -139,7 +139,9 @@ def find_point_displacement(matrix_H, pts_a, pts_b):
     pts, off, cnt, n = _pack_points(eng, pts_a, pts_b)
     H = torch.from_numpy(np.asarray(matrix_H, np.float64).reshape(1, 9)).to(eng.device)
     status = torch.zeros(1, dtype=torch.int32, device=eng.device)
-    _, _, _, flags, r = eng.static_filter(pts, off, cnt, H, status, want_r=True)
+    if n > _lib.EVZ_MAX_KP:
+        raise ValueError("at most %d point pairs are supported" % _lib.EVZ_MAX_KP)
+    _, _, _, flags, r = eng.static_filter(pts, off, cnt, H, status, want_r=True, max_cnt=n)
     if int(flags[0]):
         raise OverflowError("a displacement is not finite or exceeds %d px" % _lib.EVZ_R_MAX)
     groups = {}

@@ -45,25 +45,6 @@ def read_and_describe(capture, resize_width=400, features_type_list=None):
     return feats, shape
 
 
-def _dedup_concat(pts_list):
-    """remove_double_matching over the concatenation of several (M_i, 4) device tensors
-    (frame_processing.py:102-104): first position, last value, on exact (x, y) of the a-points."""
-    pts = torch.cat(pts_list)
-    if len(pts_list) == 1 or pts.shape[0] == 0:
-        return pts
-    a = pts[:, :2].clone()
-    a[a == 0] = 0.0                                              # -0.0 and 0.0 are the same dict key
-    bits = a.view(torch.int32).to(torch.int64)
-    key = (bits[:, 0] << 32) | (bits[:, 1] & 0xFFFFFFFF)
-    _, inv = torch.unique(key, return_inverse=True)
-    n = int(inv.max()) + 1
-    pos = torch.arange(pts.shape[0], device=pts.device)
-    first = torch.full((n,), pts.shape[0], dtype=torch.int64, device=pts.device).scatter_reduce(0, inv, pos, "amin")
-    last = torch.zeros((n,), dtype=torch.int64, device=pts.device).scatter_reduce(0, inv, pos, "amax")
-    order = torch.argsort(first)
-    return torch.cat([pts[first[order], :2], pts[last[order], 2:]], 1)
-
-
 def geometry_from_features(feats, none_H_processing=True, mode="reference", n_hyp=None, seed=None, engine=None):
     """The hot path for a whole video given per-frame features.  Returns (H_list, status): H_list[k]
     is the 3x3 matrix stored under frame k+2 (None only when the policy leaves it undefined)."""
@@ -92,7 +73,7 @@ def geometry_from_features(feats, none_H_processing=True, mode="reference", n_hy
         r = eng.match(st, np.arange(1, F), np.arange(0, F - 1))
         h1 = eng.find_homography(r.m_pts, r.out_off, r.m_cnt, r.status, st.max_kp, n_hyp, seed, 0, 1,
                                  THRESHOLD_FOR_FIND_HOMOGRAPHY, 0.0, _lib.ST_NO_MODEL_1)
-        sp, sc, _, _ = eng.static_filter(r.m_pts, r.out_off, r.m_cnt, h1["H"], r.status)
+        sp, sc, _, _ = eng.static_filter(r.m_pts, r.out_off, r.m_cnt, h1["H"], r.status, max_cnt=st.max_kp)
         status = torch.where(status == 0, r.status, status)      # any failing feature type fails the pair
         per_type.append((st, r, sp, sc))
     # level-2 input: static points of all feature types, concatenated + de-duplicated per pair
@@ -102,23 +83,18 @@ def geometry_from_features(feats, none_H_processing=True, mode="reference", n_hy
         max_cnt = st.max_kp
         cnt2 = torch.where(status == 0, cnt2, torch.zeros_like(cnt2))
     else:
-        chunks, offs, cnts, o = [], [], [], 0
-        cnt_h = [sc.cpu().numpy() for (_, _, _, sc) in per_type]
-        st_h = status.cpu().numpy()
-        for p in range(P):
-            if st_h[p] == 0:
-                parts = [sp[int(st.row_off_h[p + 1]):int(st.row_off_h[p + 1]) + int(c[p])]
-                         for (st, _, sp, _), c in zip(per_type, cnt_h)]
-                merged = _dedup_concat(parts)
-            else:
-                merged = torch.zeros((0, 4), dtype=torch.float32, device=dev)
-            pad = (-merged.shape[0]) % 4 + 4
-            chunks += [merged, torch.zeros((pad, 4), dtype=torch.float32, device=dev)]
-            offs.append(o); cnts.append(merged.shape[0]); o += merged.shape[0] + pad
-        pts2 = torch.cat(chunks)
-        off2 = torch.tensor(offs, dtype=torch.int32, device=dev)
-        cnt2 = torch.tensor(cnts, dtype=torch.int32, device=dev)
-        max_cnt = max(max(cnts), 4)
+        # frame_processing.py:91-104 on the device (evz_concat_dedup): pair p may hold up to the sum over the types
+        # of the query frame's keypoints -- known on the host, so the layout needs no read-back
+        cap = np.zeros(P, np.int64)
+        for st, _, _, _ in per_type:
+            cap += st.n_kp_h[1:].astype(np.int64)
+        cap = (cap + 3) // 4 * 4 + 4
+        off_h = np.zeros(P, np.int64)
+        np.cumsum(cap[:-1], out=off_h[1:])
+        max_cnt = max(int(sum(st.max_kp for st, _, _, _ in per_type)), 4)
+        off2 = torch.from_numpy(off_h.astype(np.int32)).to(dev)
+        pts2, cnt2 = eng.concat_dedup([(sp, r.out_off, sc) for _, r, sp, sc in per_type], status, off2,
+                                      int(cap.sum()), max_cnt)
     if mode == "parallel":
         h2 = eng.find_homography(pts2, off2, cnt2, status, max_cnt, n_hyp, seed, 0, 2, THRESHOLD_FOR_FIND_HOMOGRAPHY,
                                  LENGTH_ACCOUNTED_POINTS, _lib.ST_NO_MODEL_2)
@@ -128,19 +104,34 @@ def geometry_from_features(feats, none_H_processing=True, mode="reference", n_hy
         return [Hf[k] for k in range(P)], st_h
     if mode != "reference":
         raise ValueError("mode must be 'reference' or 'parallel'")
-    # reference-exact serial chain (video_processing.py:67-105)
+    # reference-exact serial chain (video_processing.py:67-105): RANSAC #2 of pair k sees its points through the
+    # running superposition, so the pairs go one by one.  Everything a pair needs is allocated once (single-pair
+    # views of the point store); per pair: one launch pair and one small read-back (status + H).
     H_list, st_out = [], np.zeros(P, np.int32)
+    st_in = status.cpu().numpy()
     S, H_prev, first = None, None, True
+    pre = torch.zeros((1, 9), dtype=torch.float64, device=dev)
+    pre_h = torch.zeros((1, 9), dtype=torch.float64).pin_memory()
+    res = torch.zeros((1, 10), dtype=torch.float64, device=dev)          # H (9) + status
+    res_h = torch.zeros((1, 10), dtype=torch.float64).pin_memory()
+    s_k = torch.zeros(1, dtype=torch.int32, device=dev)
     for k in range(P):
-        s_k = status[k:k + 1].clone()
         H = None
-        if int(s_k[0]) == 0:
-            pre = None if S is None else torch.from_numpy(np.asarray(S, np.float64).reshape(1, 9)).to(dev)
+        st_out[k] = st_in[k]
+        if st_in[k] == 0:
+            s_k.zero_()
+            if S is not None:
+                pre_h.copy_(torch.from_numpy(np.asarray(S, np.float64).reshape(1, 9)))
+                pre.copy_(pre_h, non_blocking=True)
             h2 = eng.find_homography(pts2, off2[k:k + 1], cnt2[k:k + 1], s_k, max_cnt, n_hyp, seed, k, 2,
-                                     THRESHOLD_FOR_FIND_HOMOGRAPHY, LENGTH_ACCOUNTED_POINTS, _lib.ST_NO_MODEL_2, pre_H=pre)
-            if int(s_k[0]) == 0:
-                H = h2["H"][0].cpu().numpy().reshape(3, 3)
-        st_out[k] = int(s_k[0])
+                                     THRESHOLD_FOR_FIND_HOMOGRAPHY, LENGTH_ACCOUNTED_POINTS, _lib.ST_NO_MODEL_2,
+                                     pre_H=None if S is None else pre, light=True)
+            res[0, :9] = h2["H"][0]
+            res[0, 9] = s_k[0]
+            res_h.copy_(res)                                         # one synchronising read-back per pair
+            st_out[k] = int(res_h[0, 9])
+            if st_out[k] == 0:
+                H = res_h[0, :9].numpy().reshape(3, 3).copy()
         if H is None:
             if none_H_processing:
                 H = H_prev                       # the reference reuses the previous pair's matrix (:95-96)

@@ -68,6 +68,7 @@ extern "C" {
 
 /* flags written by evz_static_filter into flags[p] */
 #define EVZ_FLAG_DISP_OVERFLOW 1 /* a displacement was non-finite or > EVZ_R_MAX (reference round() raises) */
+#define EVZ_FLAG_TOO_MANY_POINTS 2 /* cnt[p] > EVZ_MAX_KP although max_cnt promised otherwise: nothing was written */
 
 typedef struct evz_handle evz_handle;
 
@@ -179,11 +180,27 @@ int evz_find_homography(evz_handle* h, const float* pts, const int32_t* off, con
  *   out_pts DEV float [rows][4] kept point pairs (order preserved), out_cnt DEV int32 [P],
  *   best_r  DEV int32 [P] the winning rounded displacement, flags DEV int32 [P] (EVZ_FLAG_*)
  *   r_out   DEV int32 [rows] or NULL: round(||H a - b||) of every point (find_point_displacement's key)
+ *   max_cnt upper bound of cnt[] known to the host; > EVZ_MAX_KP -> EVZ_E_UNSUPPORTED (like evz_find_homography)
  */
 int evz_static_filter(evz_handle* h, const float* pts, const int32_t* off, const int32_t* cnt, int n_pairs,
-                      const double* H, const int32_t* status,
+                      int max_cnt, const double* H, const int32_t* status,
                       float* out_pts, int32_t* out_cnt, int32_t* best_r, int32_t* flags, int32_t* r_out,
                       void* stream);
+
+/* ---- K5b: static points of several feature types, concatenated and de-duplicated per pair.  Replaces the tail of
+ * FrameProcessing.concatenate_all_features_types (frame_processing.py:91-104: extend over the feature types, then
+ * remove_double_matching, utils.py:41-68): the a-points of pair p are the keys in first-occurrence order over
+ * type 0, type 1, ...; the b-point kept for a key is that of its LAST occurrence.
+ *   n_types <= EVZ_MAX_TYPES; pts[t] DEV float [rows_t][4], off[t] / cnt[t] DEV int32 [P] (HOST arrays of device pointers)
+ *   status  DEV int32 [P] non-zero: the pair produces no points
+ *   out_off DEV int32 [P] first output row of pair p (capacity >= sum over t of cnt[t][p]); max_total: host-known upper
+ *           bound of that sum, > EVZ_MAX_KP -> EVZ_E_UNSUPPORTED
+ *   out_pts DEV float [out rows][4], out_cnt DEV int32 [P]
+ */
+#define EVZ_MAX_TYPES 4
+int evz_concat_dedup(evz_handle* h, int n_types, const float* const* pts, const int32_t* const* off, const int32_t* const* cnt,
+                     int n_pairs, const int32_t* status, int max_total, const int32_t* out_off,
+                     float* out_pts, int32_t* out_cnt, void* stream);
 
 /* ---- K6: None-H fallback + cumulative superposition as a parallel prefix product.
  * Replaces video_processing.py:94-103 and matrix_superposition / superposition_dict

@@ -200,3 +200,29 @@ def test_exact_pruning_equals_scoring_every_hypothesis(engine, level):
     for i in (0, 1, 2, 7, 13):
         ref = ransac.find_homography_seeded(sets[i][0], sets[i][1], 700, 9, 1000 + i, level)
         assert int(f["best_hyp"][i]) == ref["hyp"]["best"] and int(f["best_cnt"][i]) == ref["hyp"]["best_count"]
+
+
+@pytest.mark.parametrize("n,out_frac,n_hyp,level", [(4915, 0.2, 1024, 1), (4915, 0.0, 1024, 2), (1229, 0.8, 4096, 1),
+                                                     (12288, 0.3, 512, 1), (2600, 0.8, 4096, 1)])
+def test_find_homography_at_baseline_config_sizes(engine, n, out_frac, n_hyp, level):
+    """Sizes of BASELINE configs 3 (8192 keypoints -> ~4 900 matches x 1 024 hypotheses) and 4 (~1 200 matches, 80 %
+    outliers, 4 096 hypotheses), and the largest supported point set: winning hypothesis, its count, its f64 model
+    and its inlier mask bit-exact against the oracle (criterion b), final H within 1e-3 px (criterion c)."""
+    rng = np.random.default_rng(n + n_hyp + level)
+    sets = [_mk(rng, n, out_frac), _mk(rng, n - 37, out_frac)]
+    pts, off, cnt, off_h, cnt_h = _pack(sets, engine.device)
+    status = torch.zeros(len(sets), dtype=torch.int32, device=engine.device)
+    out = engine.find_homography(pts, off, cnt, status, int(cnt_h.max()), n_hyp, 5, 300, level, 3.0, 0.0, 4)
+    st = status.cpu().numpy()
+    for i, (a, b) in enumerate(sets):
+        ref = ransac.find_homography_seeded(a, b, n_hyp, 5, 300 + i, level, 3.0)
+        assert st[i] == ref["status"], (i, st[i], ref["status"])
+        if ref["status"] != 0:
+            continue
+        o, m = off_h[i], cnt_h[i]
+        assert int(out["best_hyp"][i]) == ref["hyp"]["best"] and int(out["best_cnt"][i]) == ref["hyp"]["best_count"], i
+        assert np.array_equal(out["H_best"][i].cpu().numpy(), ref["hyp"]["H_all"][ref["hyp"]["best"]]), i
+        assert np.array_equal(out["mask_best"][o:o + m].cpu().numpy().astype(bool), ref["mask_best"]), i
+        inl = ref["mask_best"]
+        err = np.linalg.norm(_px(out["H"][i].cpu().numpy(), a[inl]) - _px(ref["H"], a[inl]), axis=1).mean()
+        assert err < 1e-3, (i, err)

@@ -122,3 +122,56 @@ def test_parallel_chain_equals_reference_left_fold(bundled):
     Hf = chain.fixed_plane_H(S)
     Href = np.array([hd[k]["H"] for k in keys])
     assert np.abs(Hf - Href).max() < 1e-8
+
+
+# ---------------------------------------------------------------- whole bundled clip, SIFT + ORB (BASELINE config 1)
+def _clip():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "clip_full.npz"))
+
+
+def test_orb_match_kps_matches_reference():
+    clip = _clip()
+    for p in range(12):
+        r = matching.match_kps(clip[f"orb{p+1}_c"], clip[f"orb{p+1}_d"], clip[f"orb{p}_c"], clip[f"orb{p}_d"])
+        assert np.array_equal(r["pts_a"], clip[f"orbmk{p}_pts_a"]) and np.array_equal(r["pts_b"], clip[f"orbmk{p}_pts_b"]), p
+
+
+def test_multi_type_chain_agrees_with_reference_get_homography_dict():
+    """oracle.pipeline.video_chain_multi (seeded RANSAC) against the reference's own get_homography_dict on the bundled
+    clip with ["SIFT", "ORB"] (cv2's own sampling): the merged static sets overlap almost entirely and the fixed-plane
+    chains stay within a pixel of each other -- agreement, not identity (the hypotheses differ)."""
+    from oracle import pipeline
+    clip = _clip()
+    n = 13
+    feats = {t: [(clip[f"{t.lower()}{f}_c"], clip[f"{t.lower()}{f}_d"]) for f in range(n)] for t in ("SIFT", "ORB")}
+    out = pipeline.video_chain_multi(feats, n_hyp=1024, seed=0, reference_exact=True)
+    assert (out["status"] == 0).all()
+    jac = []
+    for p in range(n - 1):
+        a = {tuple(x) for x in out["static"][p][0].tolist()}
+        b = {tuple(x) for x in clip[f"ref_cat{p}_a"].tolist()}
+        jac.append(len(a & b) / len(a | b))
+    # (the static filter keeps one bin of ROUNDED displacements: a slightly different H1 moves points across the
+    # rounding boundary, so the sets of two correct RANSAC runs overlap largely, not entirely)
+    assert min(jac) > 0.5 and np.mean(jac) > 0.75, jac
+    grid = np.stack(np.meshgrid(np.linspace(0, 400, 9), np.linspace(0, 224, 6)), -1).reshape(-1, 2)
+    pg = np.c_[grid, np.ones(len(grid))]
+    sup_ref = chain.superposition_dict({k + 2: {"H": clip["ref_H"][k].tolist()} for k in range(n - 1)})
+    for k in range(n - 1):
+        u = pg @ out["S"][k + 1].T; v = pg @ np.asarray(sup_ref[k + 2], np.float64).T
+        assert np.abs(u[:, :2] / u[:, 2:] - v[:, :2] / v[:, 2:]).mean() < 1.0, k
+
+
+def test_cpu_reference_port_reproduces_reference_H(golden):
+    """bench.py's CPU arm (oracle/cpu_reference.py, kind "port") pinned to what the unmodified reference produced with
+    the same deterministic OpenCV: compute_homography(match_static_kps(...)) on the synthetic pairs and the clip."""
+    cv2 = __import__("pytest").importorskip("cv2")
+    from oracle import cpu_reference
+    for i in range(int(golden["mk_n"])):
+        cv2.setRNGSeed(0)
+        H = cpu_reference.pair_geometry_cv2(golden[f"mk{i}_qc"], golden[f"mk{i}_qd"], golden[f"mk{i}_tc"], golden[f"mk{i}_td"])
+        assert H is not None and np.array_equal(H, golden[f"mk{i}_H"]), i
+    for p in range(int(golden["clip_n"]) - 1):
+        H = cpu_reference.pair_geometry_cv2(golden[f"clip{p+1}_c"], golden[f"clip{p+1}_d"], golden[f"clip{p}_c"], golden[f"clip{p}_d"])
+        assert H is not None and np.array_equal(H, golden[f"clip{p}_H"]), p

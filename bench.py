@@ -40,12 +40,16 @@ CONFIGS = {
             pairs=100000, n_hyp=1024, outlier_frac=0.2, unmatched_frac=0.0, strong=True, remap_points=8, tile=10),
 }
 # match (prepare, build_items x2, V-space kernel, fix-up, key-space kernel for the pairs the V-space kernel cannot take),
-# filter, score+refit, static, score+refit, scan (7 kernels)
+# filter, score+refit, static, score+refit, scan (fill x3, prod x3, fixed plane)
 KERNELS_PER_STEP = 6 + 1 + 2 + 1 + 2 + 7
-KERNELS_PER_STEP_MULTI = KERNELS_PER_STEP + 7   # + the summary pass of the cross-GPU scan (fill x3, prod x3, summary)
-# dram__bytes_read.sum + dram__bytes_write.sum of one match_top2_vkernel launch at config 2 x 10 000 pairs, from the
-# ncu --set full capture profiles/r01e_prof_vkernel_raw.csv
+# sharded scan: fill x3, prod x3, summary | NCCL all-gather (not ours) | seed, apply, fixed plane
+KERNELS_PER_STEP_MULTI = 6 + 1 + 2 + 1 + 2 + 10
+# dram__bytes_read.sum + dram__bytes_write.sum of one match_top2_vkernel<0> launch (the kernel as it ships) at config 2 x
+# 10 000 pairs, from the ncu --set full capture summarised in profiles/r02_prof_vkernel_raw.csv
 MATCH_TRAFFIC_BYTES = {(2, 10000): 3515832000 + 324532480}
+# ncu --set full of the RANSAC kernels as they ship (profiles/r02_prof_score_*.csv, 2000 pairs of config 2): issue-slot
+# utilisation and warp instructions per nominal hypothesis x match evaluation (n_hyp * matches, i.e. before pruning)
+RANSAC_NCU = {"source": "profiles/README.md r02", "score_level1": {"issue_slots_pct": None, "sm_throughput_pct": None}}
 
 
 def peaks():
@@ -113,15 +117,27 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm), samples_total=len(sm_all))
 
 
-def cpu_reference_run(frames, cores, steps, warmup):
+def cpu_arm():
+    """The CPU arm: the UNMODIFIED reference from oracle/_ref (oracle/build_ref.py) when it travelled with the
+    snapshot, else the call-for-call port oracle/cpu_reference.py (pinned bit-exactly to the reference's H by
+    tests/test_oracle_golden.py)."""
+    from oracle import ref_runner
+    if ref_runner.available():
+        return ref_runner.time_pairs, "reference", ("unmodified reference (oracle/_ref: evenvizion.processing KeyPoints.match_static_kps "
+                                                    "+ compute_homography)")
     from oracle import cpu_reference
+    return cpu_reference.time_pairs, "port", "reference path restated in oracle/cpu_reference.py"
+
+
+def cpu_reference_run(frames, cores, steps, warmup):
+    time_pairs, kind, what = cpu_arm()
     times = []
     n = ok = 0
     for i in range(warmup + steps):
-        dt, n, ok = cpu_reference.time_pairs(frames, cores)
+        dt, n, ok = time_pairs(frames, cores)
         if i >= warmup:
             times.append(dt)
-    return float(np.mean(times)), n, ok
+    return float(np.mean(times)), n, ok, kind, what
 
 
 def run_reference(args, cfg):
@@ -138,15 +154,15 @@ def run_reference(args, cfg):
                           unmatched_frac=cfg["unmatched_frac"])
     desc = ch["desc"].cpu().numpy(); coords = ch["coords"].cpu().numpy()
     frames = [(coords[i], desc[i]) for i in range(sample_pairs + 1)]
-    sec, n, ok = cpu_reference_run(frames, cores, args.steps, min(args.warmup, 1))
+    sec, n, ok, kind, what = cpu_reference_run(frames, cores, args.steps, min(args.warmup, 1))
     v = n / sec
-    sample = f"{n} consecutive pairs of the same synthetic chain per step ({ok} with a valid H), {cores} single-threaded OpenCV workers"
+    sample = f"{n} consecutive pairs of the same synthetic chain per step ({ok} with a valid H), {cores} single-threaded OpenCV workers, {what}"
     print(json.dumps({
         "impl": "reference", "metric": "frame-pairs/sec (match+RANSAC H)", "value": v, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (OpenCV CPU)", "data": "synthetic",
         "config": {"workload": cfg["name"], "n_kp": cfg["n_kp"], "sample_pairs": n},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -193,12 +209,46 @@ def int8_ceiling(torch, dev):
         return None
 
 
+def parity_check(eng, st, keep, coords_h, desc_h, n_hyp, pair_base, n_pairs):
+    """Pairs 0 .. n_pairs-1 of the LAST timed step against the oracle (oracle/pipeline.pair_geometry) on the same
+    inputs: match list and both inlier masks bit-exact, static set bit-exact, H within 1e-3 px."""
+    from oracle import pipeline
+    r, h1, sp, sc, h2 = keep
+    bad = []
+    for p in range(n_pairs):
+        ref = pipeline.pair_geometry(coords_h[p + 1].numpy(), desc_h[p + 1].numpy(), coords_h[p].numpy(), desc_h[p].numpy(),
+                                     n_hyp=n_hyp, seed=0, pair_id=pair_base + p)
+        o = int(st.row_off_h[p + 1])
+        if int(r.status[p]) != ref["status"]:
+            bad.append((p, "status")); continue
+        if ref["status"] != 0:
+            continue
+        m = int(r.m_cnt[p])
+        g = r.m_pts[o:o + m].cpu().numpy()
+        if not (np.array_equal(g[:, :2], ref["match"]["pts_a"]) and np.array_equal(g[:, 2:], ref["match"]["pts_b"])):
+            bad.append((p, "match list")); continue
+        if not np.array_equal(h1["mask_best"][o:o + m].cpu().numpy().astype(bool), ref["ransac1"]["mask_best"]):
+            bad.append((p, "inlier mask 1")); continue
+        ms = int(sc[p])
+        gs = sp[o:o + ms].cpu().numpy()
+        if not (np.array_equal(gs[:, :2], ref["static_a"]) and np.array_equal(gs[:, 2:], ref["static_b"])):
+            bad.append((p, "static set")); continue
+        if not np.array_equal(h2["mask_best"][o:o + ms].cpu().numpy().astype(bool), ref["ransac2"]["mask_best"]):
+            bad.append((p, "inlier mask 2")); continue
+        q = np.c_[ref["static_a"].astype(np.float64), np.ones(ms)]
+        u = q @ h2["H"][p].cpu().numpy().reshape(3, 3).T; v = q @ ref["H"].T
+        if not np.abs(u[:, :2] / u[:, 2:] - v[:, :2] / v[:, 2:]).mean() < 1e-3:
+            bad.append((p, "H"))
+    return {"pairs": n_pairs, "ok": not bad, "against": "oracle/pipeline.pair_geometry (match list, inlier masks, static set "
+            "bit-exact; H within 1e-3 px)", "failures": bad}
+
+
 def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
     import evenvizion_b200 as evz
     from evenvizion_b200 import synth
-    from evenvizion_b200.distributed import seeds_from_summaries, all_gather_summaries
+    from evenvizion_b200.distributed import scan_sharded
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -217,58 +267,7 @@ def run_ours(args, cfg):
     if strong:
         P = P // world                      # strong scaling: the job's pairs are split over the ranks
     K = int(cfg.get("remap_points", 0))
-
-    # synthetic shard of this rank: a contiguous range of a (world * P)-pair video
-    tile = int(cfg.get("tile", 1))
-    if tile > 1 and P + 1 >= 2 * tile:
-        base_f = -(-(P + 1) // tile)
-        ch = synth.make_chain(base_f, N, seed=rank, device=dev, outlier_frac=cfg["outlier_frac"],
-                              unmatched_frac=cfg["unmatched_frac"])
-        ch = dict(desc=ch["desc"].repeat(tile, 1, 1)[:P + 1].contiguous(), coords=ch["coords"].repeat(tile, 1, 1)[:P + 1].contiguous())
-    else:
-        ch = synth.make_chain(P + 1, N, seed=rank, device=dev, outlier_frac=cfg["outlier_frac"],
-                              unmatched_frac=cfg["unmatched_frac"])
-    desc_h = torch.empty(ch["desc"].shape, dtype=torch.uint8).pin_memory()
-    coords_h = torch.empty(ch["coords"].shape, dtype=torch.float32).pin_memory()
-    desc_h.copy_(ch["desc"]); coords_h.copy_(ch["coords"])
-    torch.cuda.synchronize()
-    st = eng.ingest(ch["desc"], ch["coords"])
-    torch.cuda.synchronize()
-    st.keep = ()                            # the raw staging copies are consumed: free them (26 GB at config 5)
-    del ch
-    pq = torch.arange(1, P + 1, dtype=torch.int32, device=dev)
-    pt = torch.arange(0, P, dtype=torch.int32, device=dev)
-    pair_base = rank * P
-
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    match_ms, ransac_ms = [], []
-    if K:
-        g = torch.Generator(device=dev); g.manual_seed(99 + rank)
-        obj_pts = torch.rand((P * K, 2), generator=g, device=dev, dtype=torch.float64) * torch.tensor([1920.0, 1080.0], device=dev, dtype=torch.float64)
-        obj_frame = torch.arange(P, dtype=torch.int32, device=dev).repeat_interleave(K).contiguous()
-
-    eng.set_option(4, 1)      # EVZ_OPT_TIME_MATCH: CUDA events around the main match kernel, read back after the timed region
-    def step(timed):
-        e = [ev() for _ in range(4)] if timed else None
-        if timed: e[0].record()
-        r = eng.match(st, pq, pt)
-        if timed: e[1].record()
-        h1 = eng.find_homography(r.m_pts, r.out_off, r.m_cnt, r.status, N, n_hyp, 0, pair_base, 1, 3.0, 0.0, 4)
-        sp, sc, sr, fl = eng.static_filter(r.m_pts, r.out_off, r.m_cnt, h1["H"], r.status, max_cnt=N)
-        h2 = eng.find_homography(sp, r.out_off, sc, r.status, N, n_hyp, 0, pair_base, 2, 3.0, 0.7, 5)
-        if timed: e[2].record()
-        if world > 1:
-            _, _, summ = eng.chain_scan(h2["H"], r.status, True, want_S=False, want_summary=True)
-            sums = all_gather_summaries(summ)
-            sS, sG = seeds_from_summaries(sums, rank, True)
-            S, Hf, _ = eng.chain_scan(h2["H"], r.status, True, seed_S=torch.from_numpy(sS.reshape(9)).to(dev),
-                                      seed_G=None if sG is None else torch.from_numpy(sG.reshape(9)).to(dev))
-        else:
-            S, Hf, _ = eng.chain_scan(h2["H"], r.status, True)
-        if K:
-            fixed = eng.remap(obj_pts, obj_frame, S, 400.0 / 1920.0, 224.0 / 1080.0, False)     # frames 2.. of the shard
-        if timed: e[3].record()
-        return r, S, e
 
     def sync_all():
         torch.cuda.synchronize()
@@ -276,39 +275,105 @@ def run_ours(args, cfg):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def make_store(P, tile, shared_chain, want_host=True):
+        """Synthetic shard of this rank.  weak scaling: every rank its own chain (seed = rank).  shared_chain: ONE
+        video for the whole job -- every rank builds the same base chain (seed 0), repeats it `tile` times and keeps
+        its contiguous frame range [rank * P, rank * P + P] (one-frame halo: the last frame of a rank is the first of
+        the next)."""
+        if tile > 1:
+            total = P * world if shared_chain else P
+            base_f = -(-(total + 1) // tile)
+            ch = synth.make_chain(base_f, N, seed=0 if shared_chain else rank, device=dev, outlier_frac=cfg["outlier_frac"],
+                                  unmatched_frac=cfg["unmatched_frac"])
+            f0 = rank * P if shared_chain else 0
+            idx = (torch.arange(f0, f0 + P + 1, device=dev) % base_f)
+            ch = dict(desc=ch["desc"].index_select(0, idx), coords=ch["coords"].index_select(0, idx))
+        else:
+            ch = synth.make_chain(P + 1, N, seed=rank, device=dev, outlier_frac=cfg["outlier_frac"],
+                                  unmatched_frac=cfg["unmatched_frac"])
+        desc_h = coords_h = None
+        if want_host:
+            desc_h = torch.empty(ch["desc"].shape, dtype=torch.uint8).pin_memory()
+            coords_h = torch.empty(ch["coords"].shape, dtype=torch.float32).pin_memory()
+            desc_h.copy_(ch["desc"]); coords_h.copy_(ch["coords"])
+        torch.cuda.synchronize()
+        st = eng.ingest(ch["desc"], ch["coords"])
+        torch.cuda.synchronize()
+        st.keep = ()                        # the raw staging copies are consumed: free them (26 GB at config 5)
+        return st, desc_h, coords_h
+
+    def make_step(st, P, pair_base, K, n_hyp):
+        pq = torch.arange(1, P + 1, dtype=torch.int32, device=dev)
+        pt = torch.arange(0, P, dtype=torch.int32, device=dev)
+        obj = None
+        if K:
+            g = torch.Generator(device=dev); g.manual_seed(99 + rank)
+            obj_pts = torch.rand((P * K, 2), generator=g, device=dev, dtype=torch.float64) * torch.tensor([1920.0, 1080.0], device=dev, dtype=torch.float64)
+            obj = (obj_pts, torch.arange(P, dtype=torch.int32, device=dev).repeat_interleave(K).contiguous())
+
+        def step(timed):
+            e = [ev() for _ in range(5)] if timed else None
+            if timed: e[0].record()
+            r = eng.match(st, pq, pt)
+            if timed: e[1].record()
+            h1 = eng.find_homography(r.m_pts, r.out_off, r.m_cnt, r.status, N, n_hyp, 0, pair_base, 1, 3.0, 0.0, 4)
+            sp, sc, sr, fl = eng.static_filter(r.m_pts, r.out_off, r.m_cnt, h1["H"], r.status, max_cnt=N)
+            h2 = eng.find_homography(sp, r.out_off, sc, r.status, N, n_hyp, 0, pair_base, 2, 3.0, 0.7, 5)
+            if timed: e[2].record()
+            S, Hf = scan_sharded(eng, h2["H"], r.status, True)     # one all-gather of 160 B per rank when world > 1
+            if timed: e[3].record()
+            if obj is not None:
+                eng.remap(obj[0], obj[1], S, 400.0 / 1920.0, 224.0 / 1080.0, False)     # frames 2.. of the shard
+            if timed: e[4].record()
+            return (r, h1, sp, sc, h2), S, e
+        return step
+
+    def timed_run(step, steps, warmup):
+        for _ in range(warmup):
+            step(False)
+        sync_all()
+        t0, t1 = ev(), ev()
+        evs = []
+        w_begin = time.time()
+        t0.record()
+        for _ in range(steps):
+            keep, S, e = step(True)
+            evs.append(e)
+        t1.record()
+        sync_all()
+        w_end = time.time()
+        total_ms = t0.elapsed_time(t1)
+        stage = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in evs]).mean(0)
+        return total_ms, stage, keep, S, (w_begin, w_end)
+
+    tile = int(cfg.get("tile", 1))
+    st, desc_h, coords_h = make_store(P, tile if P + 1 >= 2 * tile else 1, strong)
+    pair_base = rank * P
+    eng.set_option(4, 1)      # EVZ_OPT_TIME_MATCH: CUDA events around the main match kernel, read back after the timed region
+    step = make_step(st, P, pair_base, K, n_hyp)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        r, S, _ = step(False)
-    sync_all()
-    t0, t1 = ev(), ev()
-    w_begin = time.time()
-    evs = []
-    t0.record()
-    for _ in range(args.steps):
-        r, S, e = step(True)
-        evs.append(e)
-    t1.record()
-    sync_all()
-    w_end = time.time()
+    total_ms, stage, keep, S, (w_begin, w_end) = timed_run(step, args.steps, max(args.warmup, 3))
     clocks = sampler.stop(w_begin, w_end) if rank == 0 else None
-    total_ms = t0.elapsed_time(t1)
-    for e in evs:
-        match_ms.append(e[0].elapsed_time(e[1])); ransac_ms.append(e[1].elapsed_time(e[2]))
     # per-launch duration of the dominant kernel (the last min(steps, 16) launches, all inside the timed region)
     kern_ms = [eng.match_kernel_ms(k) for k in range(min(args.steps, 16))]
+    r = keep[0]
     n_ok = int((r.status == 0).sum().item())
     mean_matches = float(r.m_cnt.float().mean().item())
+    mean_static = float(keep[3].float().mean().item())
+    # the timed result is checked, not just timed: first pairs of the last step against the oracle (rank 0)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_check(eng, st, keep, coords_h, desc_h, n_hyp, pair_base, min(P, 8 if N <= 4096 else 3))
     # first pairs of the last step, kept for the reported-only FLANN agreement rate (rank 0, below)
     flann_pairs = min(8, P)
     flann_rows = [(int(st.row_off_h[q]), int(st.n_kp_h[q])) for q in range(1, flann_pairs + 1)]
     flann_idx = [r.top2_idx[o:o + n, 0].cpu().numpy() for o, n in flann_rows]
     flann_surv = [r.surv[o:o + n].cpu().numpy().astype(bool) for o, n in flann_rows]
-    del r
+    del r, keep, S
 
     # ---- end to end through the public host API (pinned host buffers in, host arrays out)
-    del S
     out = None
     for _ in range(2):
         out = None
@@ -324,34 +389,87 @@ def run_ours(args, cfg):
     h2d = desc_h.numel() + coords_h.numel() * 4
     d2h = sum(out[k].nbytes for k in ("G", "status", "S", "H_fixed"))
     del out
+    # the ceiling of the host-buffer path: the same pinned buffers copied to the device and nothing else, all ranks
+    # at the same time (one cudaMemcpyAsync per buffer); e2e cannot be faster than this
+    dd = torch.empty(desc_h.shape, dtype=torch.uint8, device=dev); dc = torch.empty(coords_h.shape, dtype=torch.float32, device=dev)
+    for _ in range(2):
+        dd.copy_(desc_h, non_blocking=True); dc.copy_(coords_h, non_blocking=True)
+    sync_all()
+    w0 = time.perf_counter()
+    for _ in range(3):
+        dd.copy_(desc_h, non_blocking=True); dc.copy_(coords_h, non_blocking=True)
+    sync_all()
+    h2d_ms = (time.perf_counter() - w0) * 1e3 / 3
+    del dd, dc
 
     if world > 1:
-        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, e2e_ms, h2d_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms = float(t[0]), float(t[1])
+        total_ms, e2e_ms, h2d_ms = float(t[0]), float(t[1]), float(t[2])
     ms_per_step = total_ms / args.steps
+
+    # ---- N > 1: BASELINE config 5 (one 100 000-pair video sharded over the ranks with a one-frame halo, cumulative scan
+    # across the shards, remap of 8 object points per frame), and the sharded scan checked against the single-GPU scan
+    c5 = None
+    if world > 1 and args.config == 2 and not args.no_c5:
+        del st, step
+        torch.cuda.empty_cache()
+        c5cfg = CONFIGS[5]
+        P5 = (args.pairs * 10 if args.pairs else c5cfg["pairs"]) // world
+        st5, _, _ = make_store(P5, c5cfg["tile"], True, want_host=False)
+        step5 = make_step(st5, P5, rank * P5, c5cfg["remap_points"], c5cfg["n_hyp"])
+        t5, stage5, keep5, S5, _ = timed_run(step5, 2, 2)
+        # scan check: every rank gathers all G / status / S; the single-GPU scan over the whole video must reproduce
+        # the sharded one
+        G5, s5 = keep5[4]["H"].contiguous(), keep5[0].status.contiguous()
+        Gall = torch.empty((world * P5, 9), dtype=torch.float64, device=dev)
+        sall = torch.empty((world * P5,), dtype=torch.int32, device=dev)
+        Sall = torch.empty((world * P5, 9), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(Gall, G5); dist.all_gather_into_tensor(sall, s5); dist.all_gather_into_tensor(Sall, S5.contiguous())
+        S1, _, _ = eng.chain_scan(Gall, sall, True, want_fixed=False)
+        err = float(((S1 - Sall).abs().max() / Sall.abs().max()).item())
+        n_fail = int((sall != 0).sum().item())
+        tt = torch.tensor([t5] + list(stage5), dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t5ms = float(tt[0]) / 2
+        c5 = {"workload": c5cfg["name"], "pairs_total": world * P5, "pairs_per_gpu": P5, "scaling": "strong",
+              "pairs_s": world * P5 / (t5ms * 1e-3), "ms_per_step": t5ms, "match_ms": float(tt[1]), "ransac_ms": float(tt[2]),
+              "scan_ms": float(tt[3]), "remap_ms": float(tt[4]), "remap_points": world * P5 * c5cfg["remap_points"],
+              "failed_pairs_forward_filled": n_fail,
+              "scan_check": {"max_rel_diff_sharded_vs_single_gpu_scan": err, "tolerance": 1e-9, "ok": err <= 1e-9}}
+        if err > 1e-9:
+            raise SystemExit(f"bench.py: sharded scan differs from the single-GPU scan by {err:.3e} (relative)")
+        del st5, step5, keep5, S5, Gall, sall, Sall, S1
 
     if rank == 0:
         pk = peaks()
-        m_ms = float(np.mean(match_ms))
+        m_ms, r_ms, s_ms, rm_ms = (float(x) for x in stage)
         k_ms = float(np.mean(kern_ms))
         ops = 2.0 * N * N * 128 * P
         achieved = ops / (k_ms * 1e-3) / 1e12
         i8 = int8_ceiling(torch, dev)
-        peak = i8 if i8 else 2.0 * pk["bf16_burst"]
+        peak2 = 2.0 * pk["bf16_burst"]
         cores = os.cpu_count() or 1
         # bounded CPU baseline on the same workload (first pairs of this rank's chain)
         cpu = None
         if world == 1 and not args.no_cpu:
             sp_pairs = min(128 * cores, 2048, P)      # about 10 s of CPU work on the box's cores
             frames = [(coords_h[i].numpy(), desc_h[i].numpy()) for i in range(sp_pairs + 1)]
-            sec, n, ok = cpu_reference_run(frames, cores, 1, 0)
-            cpu = {"value": n / sec, "unit": "pairs/s", "cores": cores, "kind": "port",
+            sec, n, ok, kind, what = cpu_reference_run(frames, cores, 1, 0)
+            cpu = {"value": n / sec, "unit": "pairs/s", "cores": cores, "kind": kind,
                    "sample": f"first {n} pairs of the same chain, one pass ({sec:.1f} s), {cores} single-threaded OpenCV workers, "
-                             f"reference path restated in oracle/cpu_reference.py ({ok} pairs with a valid H)"}
+                             f"{what} ({ok} pairs with a valid H)"}
         flann = None
         if world == 1 and not args.no_cpu:
             flann = flann_agreement(desc_h, flann_idx, flann_surv)
+        if parity is not None and not parity["ok"]:
+            print(json.dumps({"error": "parity check against the oracle failed", "parity_check": parity}))
+            raise SystemExit(1)
+        alg_bytes = (P + 1) * N * (128 + 4) + P * N * 16          # descriptors + norms once per frame, top-2 out per pair
+        traffic = MATCH_TRAFFIC_BYTES.get((args.config, P))
+        evals1 = float(n_hyp) * mean_matches * P                  # nominal hypothesis x match evaluations, level 1
+        evals2 = float(n_hyp) * mean_static * P
+        scan_bytes = P * (72 + 4 + 72 + 72)                       # G + status in, S + H_fixed out
         print(json.dumps({
             "metric": "frame-pairs/sec (match+RANSAC H)", "value": world * P / (ms_per_step * 1e-3), "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
@@ -359,26 +477,37 @@ def run_ours(args, cfg):
             "dtype": "u8 (s32 accumulate) match; f32/f64 RANSAC", "data": "synthetic",
             "config": {"workload": cfg["name"], "n_kp": N, "pairs_per_gpu": P, "n_hyp": n_hyp, "parallelism": f"pair-range x{world}",
                        "l2": f"inputs {(P + 1) * N * 136 / 1e9:.1f} GB per step > 126 MB L2, no flush", "valid_pairs_last_step": n_ok,
-                       "mean_matches_per_pair": mean_matches},
-            "stage_ms": {"match": m_ms, "ransac_static_ransac": float(np.mean(ransac_ms)),
-                         "scan": ms_per_step - m_ms - float(np.mean(ransac_ms))},
-            "roofline": {"kernel": "match_top2_vkernel", "bound": "tensor",
-                         "achieved": achieved, "peak": peak, "kernel_ms": k_ms,
-                         "achieved_whole_match_stage": ops / (m_ms * 1e-3) / 1e12,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": MATCH_TRAFFIC_BYTES.get((args.config, P)),
-                         # descriptors once per frame; per pair and row: 32 B of fifth-K-block codes + parity bit of the
-                         # train frame, 4 B query norm in, 16 B top-2 out
-                         "algorithmic_bytes": (P + 1) * N * 128 + P * N * (32 + 4 + 16) + P * N // 8,
-                         "peak_source": "torch._int_mm 8192^3 measured in this run (dense int8 cuBLASLt)" if i8 else "2 x MEASURED bf16 burst",
+                       "mean_matches_per_pair": mean_matches, "mean_static_points_per_pair": mean_static},
+            "stage_ms": {"match": m_ms, "ransac_static_ransac": r_ms, "scan": s_ms, "remap": rm_ms},
+            "parity_check": parity,
+            "roofline": {"kernel": "match_top2_vkernel", "bound": "tensor", "unit": "TFLOP/s",
+                         "achieved": achieved, "peak": peak2, "frac": achieved / peak2,
+                         "peak_source": "2 x bf16_tflops of MEASURED_PEAKS.json (dense int8 = 2 x bf16 on tcgen05; the file has no int8 entry)"
+                                        if pk["source"] == "MEASURED_PEAKS.json" else "2 x fallback bf16 peak (B200_PROFILING.md)",
                          "peak_nominal_int8": 4500.0, "frac_of_nominal": achieved / 4500.0,
-                         "peak_2x_measured_bf16": 2.0 * pk["bf16_burst"], "frac_of_2x_measured_bf16": achieved / (2.0 * pk["bf16_burst"]),
-                         "ops_per_launch": ops,
-                         "note": "ops = 2*Nq*Nt*128 per pair (int8 MAC = 2 ops); the fifth K block that carries the train "
-                                 "norms (+25 % tensor work) is not counted"},
+                         "peak_int_mm_this_run": i8, "frac_of_int_mm_this_run": (achieved / i8) if i8 else None,
+                         "kernel_ms": k_ms, "ops_per_launch": ops,
+                         "achieved_whole_match_stage": ops / (m_ms * 1e-3) / 1e12,
+                         "traffic": traffic, "algorithmic_bytes": alg_bytes,
+                         "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,
+                         "note": "ops = 2*Nq*Nt*128 per pair (int8 MAC = 2 ops); the fifth K block that carries the train norms "
+                                 "(+25 % tensor work) and its 32 B/row of code bytes are implementation cost, not counted as work"},
+            "ransac": {"stage_ms": r_ms, "nominal_evals_level1": evals1, "nominal_evals_level2": evals2,
+                       "nominal_evals_per_s": (evals1 + evals2) / (r_ms * 1e-3),
+                       "bound": "SM issue (fp32)", "ncu": RANSAC_NCU,
+                       "note": "evaluations = n_hyp x points per level; exact pruning (DESIGN.md K3) executes a fraction of them"},
+            "scan": {"ms": s_ms, "bytes": scan_bytes, "gbs": scan_bytes / (s_ms * 1e-3) / 1e9, "peak_gbs": pk["hbm_gbs"],
+                     "frac": scan_bytes / (s_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "bound": "launch latency at this size (7 launches, 2 MB)"},
+            "remap": ({"ms": rm_ms, "points": P * K, "bytes": P * K * 36, "gbs": P * K * 36 / (rm_ms * 1e-3) / 1e9,
+                       "frac": P * K * 36 / (rm_ms * 1e-3) / 1e9 / pk["hbm_gbs"]} if K else None),
             "cpu_baseline": cpu,
             "flann_agreement": flann,
             "e2e": {"value": world * P / (e2e_ms * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms,
+                    "h2d_only_ms": h2d_ms, "h2d_only_gbs_per_gpu": h2d / (h2d_ms * 1e-3) / 1e9,
+                    "frac_of_h2d_ceiling": h2d_ms / e2e_ms,
+                    "note": "h2d_only = the same pinned buffers copied to the device and nothing else, all ranks at once: the ceiling of the host-buffer path"},
+            "config5_strong": c5,
             "gpu_launches": ((KERNELS_PER_STEP_MULTI if world > 1 else KERNELS_PER_STEP) + (1 if K else 0)) * args.steps,
             "clocks": clocks, "peaks": pk,
         }))
@@ -395,6 +524,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--pairs", type=int, default=0, help="override pairs per GPU (debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the bounded CPU baseline")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the last timed step")
+    ap.add_argument("--no-c5", action="store_true", help="N > 1: skip the sharded 100k-pair video (config 5) and its scan check")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":

@@ -292,6 +292,42 @@ __global__ void summary_kernel(const double* __restrict__ G, const int32_t* __re
     summary[19] = last >= 0 ? 1.0 : 0.0;
 }
 
+// ---- cross-GPU seeding on the device (port of evenvizion_b200/distributed.py::seeds_from_summaries).
+// summaries: [world][20] as written by summary_kernel on every rank and all-gathered.  Single thread:
+//   seed_S  superposition before this rank's first pair, seed_G last valid step before it (identity when there is none,
+//           which is what an absent seed means to the fill), A = seed_S . seed_G^lead = the factor that turns this rank's
+//           UNSEEDED local scan into the global one from its first valid pair on (lead = its number of leading
+//           invalid pairs); the first `lead` rows of S (S_k = seed_S . seed_G^(k+1)) are written here, serially.
+// seeds_out: [27] = seed_S | seed_G | A
+__global__ void seed_kernel(const double* __restrict__ summaries, int world, int rank, int policy, int n,
+                            double* __restrict__ S, double* __restrict__ seeds_out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    M3 Sm = m3_identity(), lastG = m3_identity();
+    bool have = false;
+    for (int r = 0; r < rank; ++r) {
+        const double* s = summaries + static_cast<size_t>(r) * 20;
+        const int lead = static_cast<int>(s[18] + 0.5);
+        if (policy != 0 && have)
+            for (int i = 0; i < lead; ++i) Sm = m3_mul_norm(Sm, lastG);       // leading failures of shard r repeat the carried step
+        if (s[19] > 0.5) { Sm = m3_mul_norm(Sm, m3_load(s)); lastG = m3_load(s + 9); have = true; }
+    }
+    const M3 G = (policy != 0 && have) ? lastG : m3_identity();
+    m3_store(seeds_out, Sm);
+    m3_store(seeds_out + 9, G);
+    const int lead = min(n, static_cast<int>(summaries[static_cast<size_t>(rank) * 20 + 18] + 0.5));
+    M3 A = Sm;
+    for (int k = 0; k < lead; ++k) { A = m3_mul_norm(A, G); m3_store(S + static_cast<size_t>(k) * 9, A); }
+    m3_store(seeds_out + 18, A);
+}
+// S[k] = normalise(A . S_local[k]) for the pairs from the first valid one on
+__global__ void __launch_bounds__(kScanBlock)
+seed_apply_kernel(double* __restrict__ S, const double* __restrict__ summaries, int rank, const double* __restrict__ seeds, int n) {
+    const int k = blockIdx.x * kScanBlock + threadIdx.x;
+    const int lead = static_cast<int>(summaries[static_cast<size_t>(rank) * 20 + 18] + 0.5);
+    if (k >= n || k < lead) return;
+    m3_store(S + static_cast<size_t>(k) * 9, m3_mul_norm(m3_load(seeds + 18), m3_load(S + static_cast<size_t>(k) * 9)));
+}
+
 // ------------------------------------------------------------------------------------ K7
 __global__ void __launch_bounds__(256)
 remap_kernel(const double* __restrict__ pin, const int32_t* __restrict__ frame_idx, int64_t n,
@@ -401,7 +437,8 @@ extern "C" int evz_chain_scan(evz_handle* h, const double* G, const int32_t* sta
     EVZ_LAUNCH_CHECK(h);
     evz::fill_apply_kernel<<<nb, evz::kScanBlock, 0, st>>>(src, block_carry, n_pairs);
     EVZ_LAUNCH_CHECK(h);
-    if (summary) {
+    const bool seeded = seed_S != nullptr || seed_G != nullptr;
+    if (summary || (S && !seeded)) {
         // unseeded pass: leading invalid pairs are identity steps, so the total is R
         evz::prod_local_kernel<<<nb, evz::kScanBlock, 0, st>>>(G, src, n_pairs, policy, nullptr, S_work, block_tot);
         EVZ_LAUNCH_CHECK(h);
@@ -409,20 +446,41 @@ extern "C" int evz_chain_scan(evz_handle* h, const double* G, const int32_t* sta
         EVZ_LAUNCH_CHECK(h);
         evz::prod_apply_kernel<<<nb, evz::kScanBlock, 0, st>>>(S_work, block_pre, n_pairs, 0);
         EVZ_LAUNCH_CHECK(h);
-        evz::summary_kernel<<<1, 32, 0, st>>>(G, src, S_work + static_cast<size_t>(n_pairs - 1) * 9, n_pairs, summary);
-        EVZ_LAUNCH_CHECK(h);
+        if (summary) {
+            evz::summary_kernel<<<1, 32, 0, st>>>(G, src, S_work + static_cast<size_t>(n_pairs - 1) * 9, n_pairs, summary);
+            EVZ_LAUNCH_CHECK(h);
+        }
     }
-    if (S) {
+    if (S && seeded) {
         evz::prod_local_kernel<<<nb, evz::kScanBlock, 0, st>>>(G, src, n_pairs, policy, seed_G, S, block_tot);
         EVZ_LAUNCH_CHECK(h);
         evz::prod_carry_kernel<<<1, evz::kScanBlock, 0, st>>>(block_tot, nb, seed_S, block_pre);
         EVZ_LAUNCH_CHECK(h);
         evz::prod_apply_kernel<<<nb, evz::kScanBlock, 0, st>>>(S, block_pre, n_pairs, seed_S ? 1 : 0);
         EVZ_LAUNCH_CHECK(h);
-        if (H_fixed) {
-            evz::fixed_plane_kernel<<<nb, evz::kScanBlock, 0, st>>>(S, seed_S, n_pairs, H_fixed);
-            EVZ_LAUNCH_CHECK(h);
-        }
+    }
+    if (S && H_fixed) {
+        evz::fixed_plane_kernel<<<nb, evz::kScanBlock, 0, st>>>(S, seed_S, n_pairs, H_fixed);
+        EVZ_LAUNCH_CHECK(h);
+    }
+    return EVZ_OK;
+}
+
+extern "C" int evz_chain_seed_apply(evz_handle* h, const double* summaries, int world, int rank, int policy, int n_pairs,
+                                    double* S, double* H_fixed, double* seeds_out, void* stream) {
+    if (!h) return EVZ_E_ARG;
+    EVZ_REQUIRE(h, summaries && S && seeds_out, "null pointer");
+    EVZ_REQUIRE(h, world >= 1 && rank >= 0 && rank < world, "rank must be in [0, world)");
+    if (n_pairs <= 0) return EVZ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nb = (n_pairs + evz::kScanBlock - 1) / evz::kScanBlock;
+    evz::seed_kernel<<<1, 32, 0, st>>>(summaries, world, rank, policy, n_pairs, S, seeds_out);
+    EVZ_LAUNCH_CHECK(h);
+    evz::seed_apply_kernel<<<nb, evz::kScanBlock, 0, st>>>(S, summaries, rank, seeds_out, n_pairs);
+    EVZ_LAUNCH_CHECK(h);
+    if (H_fixed) {
+        evz::fixed_plane_kernel<<<nb, evz::kScanBlock, 0, st>>>(S, seeds_out, n_pairs, H_fixed);
+        EVZ_LAUNCH_CHECK(h);
     }
     return EVZ_OK;
 }

@@ -47,3 +47,20 @@ def all_gather_summaries(summary, group=None):
     bufs = [torch.empty_like(summary) for _ in range(world)]
     dist.all_gather(bufs, summary, group=group)
     return [b.cpu().numpy() for b in bufs]
+
+
+def scan_sharded(eng, G, status, policy=True, group=None, want_fixed=True):
+    """Cumulative superposition of a video whose pairs are sharded over the ranks of `group`, without leaving the
+    device: unseeded local scan + 20-double summary (evz_chain_scan), ONE all-gather of the summaries
+    (`all_gather_into_tensor`: NCCL over NVLink), then evz_chain_seed_apply.  Returns (S, H_fixed) of this rank's pairs."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        S, Hf, _ = eng.chain_scan(G, status, policy, want_fixed=want_fixed)
+        return S, Hf
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    S, _, summ = eng.chain_scan(G, status, policy, want_fixed=False, want_summary=True)
+    buf = torch.empty((world, 20), dtype=torch.float64, device=summ.device)
+    dist.all_gather_into_tensor(buf, summ, group=group)
+    S, Hf, _ = eng.chain_seed_apply(buf, rank, S, policy, want_fixed)
+    return S, Hf

@@ -306,7 +306,21 @@ class GeometryEngine:
         if P:
             self._check(self.lib.evz_chain_scan(self.h, _ptr(G), _ptr(status), P, 1 if policy else 0, _ptr(seed_S), _ptr(seed_G),
                                                 _ptr(S), _ptr(Hf), _ptr(summ), self._stream()))
+        elif summ is not None:       # an empty shard: identity product, no valid pair
+            summ.copy_(torch.tensor([1, 0, 0, 0, 1, 0, 0, 0, 1] * 2 + [0, 0], dtype=torch.float64))
         return S, Hf, summ
+
+    def chain_seed_apply(self, summaries, rank, S, policy=True, want_fixed=True):
+        """Turn this rank's unseeded local scan S ([P,9], in place) into its slice of the global scan, given the
+        all-gathered shard summaries ([world,20] device tensor).  Returns (S, H_fixed or None, seeds [27])."""
+        world = int(summaries.shape[0])
+        P = int(S.shape[0])
+        Hf = self._empty((P, 9), torch.float64) if want_fixed else None
+        seeds = self._empty((27,), torch.float64)
+        if P:
+            self._check(self.lib.evz_chain_seed_apply(self.h, _ptr(summaries), world, int(rank), 1 if policy else 0, P,
+                                                      _ptr(S), _ptr(Hf), _ptr(seeds), self._stream()))
+        return S, Hf, seeds
 
     def remap(self, pts, frame_idx, S, sx, sy, inverse=False):
         pts = pts.reshape(-1, 2).contiguous()

@@ -223,6 +223,16 @@ int evz_chain_scan(evz_handle* h, const double* G, const int32_t* status, int n_
                    const double* seed_S, const double* seed_G,
                    double* S, double* H_fixed, double* summary, void* stream);
 
+/* ---- K6b: cross-GPU seeding of the scan, on the device (no host round trip).  Every rank calls evz_chain_scan with
+ * S and summary (no seeds: an UNSEEDED local scan), all-gathers the 20-double summaries into `summaries`
+ * (ncclAllGather / torch.distributed.all_gather_into_tensor), then calls this: S becomes the rank's slice of the global
+ * scan (identical to evz_chain_scan over the whole video up to the rounding of a different association order).
+ *   summaries DEV double [world][20]; S DEV double [P][9] in: unseeded local scan, out: global scan
+ *   H_fixed   DEV double [P][9] or NULL;  seeds_out DEV double [27]: seed_S | seed_G | seed_S . seed_G^lead
+ */
+int evz_chain_seed_apply(evz_handle* h, const double* summaries, int world, int rank, int policy, int n_pairs,
+                         double* S, double* H_fixed, double* seeds_out, void* stream);
+
 /* ---- K7: object-coordinate remap.  Replaces from_original_to_fix / from_fix_to_original
  * (fixed_coordinate_system.py:19-122): (x', y') = around(T . (sx*x, sy*y, 1), 2) with
  * T = S[frame] (inverse = 0) or S[frame]^-1 (inverse = 1).

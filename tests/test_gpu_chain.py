@@ -80,6 +80,22 @@ def test_scan_with_failures_and_shards(engine, policy):
         Sr, _, _ = engine.chain_scan(Gd[a:b], st[a:b], policy, seed_S=torch.from_numpy(seed_S.reshape(9)).to(dev),
                                      seed_G=None if seed_G is None else torch.from_numpy(seed_G.reshape(9)).to(dev))
         assert np.abs(Sr.cpu().numpy().reshape(-1, 3, 3) - ref[a:b]).max() < 1e-6 * np.abs(ref).max(), r
+    # the same on the device, without a host round trip (evz_chain_seed_apply): unseeded local scans + the gathered
+    # summaries; the seeds it derives equal the host formula, S and H_fixed equal the single-GPU scan
+    locals_, sums = [], []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        Sl, _, sm = engine.chain_scan(Gd[a:b], st[a:b], policy, want_fixed=False, want_summary=True)
+        locals_.append(Sl); sums.append(sm)
+    gathered = torch.stack(sums)
+    assert np.array_equal(gathered.cpu().numpy(), np.array(summaries))
+    for r, (a, b) in enumerate(zip(bounds[:-1], bounds[1:])):
+        Sr, Hr, seeds = engine.chain_seed_apply(gathered, r, locals_[r], policy)
+        seed_S, seed_G = seeds_from_summaries(summaries, r, policy)
+        sd = seeds.cpu().numpy()
+        assert np.abs(sd[:9].reshape(3, 3) - seed_S).max() < 1e-9 * np.abs(seed_S).max(), r
+        assert np.abs(sd[9:18].reshape(3, 3) - (np.eye(3) if seed_G is None else seed_G)).max() < 1e-12, r
+        assert np.abs(Sr.cpu().numpy().reshape(-1, 3, 3) - ref[a:b]).max() < 1e-9 * np.abs(ref).max(), r
+        assert np.abs(Hr.cpu().numpy() - Hf[a:b].cpu().numpy()).max() < 1e-9, r
 
 
 def test_pipeline_vs_oracle_synthetic(engine):

@@ -343,7 +343,10 @@ def run_ours(args, cfg):
         sync_all()
         w_end = time.time()
         total_ms = t0.elapsed_time(t1)
-        stage = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in evs]).mean(0)
+        per_step = np.array([[e[i].elapsed_time(e[i + 1]) for i in range(4)] for e in evs])
+        if os.environ.get("EVZ_BENCH_DEBUG"):
+            print(f"[rank {rank}] per-step stage ms:\n{np.round(per_step, 3)}", file=sys.stderr, flush=True)
+        stage = per_step.mean(0)
         return total_ms, stage, keep, S, (w_begin, w_end)
 
     tile = int(cfg.get("tile", 1))
@@ -355,6 +358,8 @@ def run_ours(args, cfg):
     if rank == 0:
         sampler.start()
     total_ms, stage, keep, S, (w_begin, w_end) = timed_run(step, args.steps, max(args.warmup, 3))
+    if os.environ.get("EVZ_BENCH_DEBUG"):
+        print(f"[rank {rank}] total {total_ms / args.steps:.3f} ms/step, stages {[round(float(x), 3) for x in stage]}", file=sys.stderr, flush=True)
     clocks = sampler.stop(w_begin, w_end) if rank == 0 else None
     # per-launch duration of the dominant kernel (the last min(steps, 16) launches, all inside the timed region)
     kern_ms = [eng.match_kernel_ms(k) for k in range(min(args.steps, 16))]

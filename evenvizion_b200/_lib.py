@@ -29,6 +29,7 @@ SIGNATURES = {
     "evz_match_kernel_ms": [_p, _i, C.POINTER(C.c_float)],
     "evz_ingest": [_p, _p, _i, _i, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p],
     "evz_match_top2": [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _i, _p, _p, _p],
+    "evz_match_top2_d": [_p, _p, _i, _p, _i64, _p, _p, _p, _p, _p, _i, _p, _p, _p],
     "evz_filter_matches": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _d, _i, _p, _p, _p, _p, _p, _p, _p],
     "evz_find_homography": [_p, _p, _p, _p, _i, _i, _p, _i, C.c_uint32, _i64, _i, _d, _d, _i,
                             _p, _p, _p, _p, _p, _p, _p, _p, _p],

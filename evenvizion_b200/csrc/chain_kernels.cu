@@ -135,19 +135,36 @@ struct M3 { double m[9]; };
 __device__ __forceinline__ M3 m3_identity() { M3 r; for (int i = 0; i < 9; ++i) r.m[i] = (i % 4 == 0) ? 1.0 : 0.0; return r; }
 __device__ __forceinline__ M3 m3_load(const double* p) { M3 r; for (int i = 0; i < 9; ++i) r.m[i] = p[i]; return r; }
 __device__ __forceinline__ void m3_store(double* p, const M3& a) { for (int i = 0; i < 9; ++i) p[i] = a.m[i]; }
-// normalise(a . b): the reference divides the running product by its [2][2] at every step
-__device__ __forceinline__ M3 m3_mul_norm(const M3& a, const M3& b) {
+// a . b inside the scan.  The reference divides the running product by its [2][2] at every step (utils.py:139-145);
+// a homography is defined up to scale, so only the matrices that are STORED need that normalisation.  Inside the
+// tree the partial products (G3 . G4, block totals: products the reference never forms) are kept in range by an
+// exact power-of-two scale instead -- a partial product whose [2][2] happens to be ~0 must not poison its prefix.
+__device__ __forceinline__ M3 m3_mul_scaled(const M3& a, const M3& b) {
     M3 r;
+    double mx = 0.0;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int j = 0; j < 3; ++j)
+        for (int j = 0; j < 3; ++j) {
             r.m[3 * i + j] = (a.m[3 * i] * b.m[j] + a.m[3 * i + 1] * b.m[3 + j]) + a.m[3 * i + 2] * b.m[6 + j];
-    const double s = r.m[8];
+            mx = fmax(mx, fabs(r.m[3 * i + j]));
+        }
+    if (mx > 0.0 && mx < 1.0 / 0.0) {
+        const int e = -ilogb(mx);
 #pragma unroll
-    for (int i = 0; i < 9; ++i) r.m[i] = r.m[i] / s;
+        for (int i = 0; i < 9; ++i) r.m[i] = scalbn(r.m[i], e);
+    }
     return r;
 }
+__device__ __forceinline__ M3 m3_norm22(const M3& a) {
+    M3 r;
+    const double s = a.m[8];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) r.m[i] = a.m[i] / s;
+    return r;
+}
+// normalise(a . b), for the few products that are stored directly
+__device__ __forceinline__ M3 m3_mul_norm(const M3& a, const M3& b) { return m3_norm22(m3_mul_scaled(a, b)); }
 __device__ __forceinline__ M3 m3_inverse(const M3& a) {
     const double* m = a.m;
     M3 r;
@@ -218,16 +235,16 @@ prod_local_kernel(const double* __restrict__ G, const int32_t* __restrict__ src,
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const M3 t = m3_shfl_up(v, d);
-        if (lane >= d) v = m3_mul_norm(t, v);
+        if (lane >= d) v = m3_mul_scaled(t, v);
     }
     if (lane == 31) m3_store(wt[warp], v);
     __syncthreads();
     if (warp > 0) {
         M3 c = m3_load(wt[0]);
-        for (int w = 1; w < warp; ++w) c = m3_mul_norm(c, m3_load(wt[w]));
-        v = m3_mul_norm(c, v);
+        for (int w = 1; w < warp; ++w) c = m3_mul_scaled(c, m3_load(wt[w]));
+        v = m3_mul_scaled(c, v);
     }
-    if (k < n) m3_store(S + static_cast<size_t>(k) * 9, v);
+    if (k < n) m3_store(S + static_cast<size_t>(k) * 9, m3_norm22(v));         // a true prefix of the (shard's) chain
     if (threadIdx.x == kScanBlock - 1) m3_store(block_tot + static_cast<size_t>(blockIdx.x) * 9, v);
 }
 // phase B2 (single CTA): exclusive prefix of the block totals, seeded.  Block-wide shuffle scan over
@@ -245,13 +262,13 @@ prod_carry_kernel(const double* __restrict__ block_tot, int nb, const double* __
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const M3 t = m3_shfl_up(v, d);
-            if (lane >= d) v = m3_mul_norm(t, v);
+            if (lane >= d) v = m3_mul_scaled(t, v);
         }
         if (lane == 31) m3_store(wt[warp], v);
         __syncthreads();
         M3 c = carry;
-        for (int w = 0; w < warp; ++w) c = m3_mul_norm(c, m3_load(wt[w]));
-        const M3 incl = m3_mul_norm(c, v);                       // inclusive prefix through block b
+        for (int w = 0; w < warp; ++w) c = m3_mul_scaled(c, m3_load(wt[w]));
+        const M3 incl = m3_mul_scaled(c, v);                       // inclusive prefix through block b
         // exclusive prefix = inclusive prefix of the previous block
         M3 excl = m3_shfl_up(incl, 1);
         if (lane == 0) excl = c;
@@ -392,6 +409,7 @@ extern "C" int evz_static_filter(evz_handle* h, const float* pts, const int32_t*
                                  float* out_pts, int32_t* out_cnt, int32_t* best_r, int32_t* flags, int32_t* r_out,
                                  void* stream) {
     if (!h) return EVZ_E_ARG;
+    EVZ_ENTER(h);
     EVZ_REQUIRE(h, pts && off && cnt && H && status && out_pts && out_cnt && best_r && flags, "null pointer");
     if (max_cnt > EVZ_MAX_KP) {
         EVZ_SET_ERR(h, "evz_static_filter: max_cnt %d exceeds the supported %d points per pair", max_cnt, EVZ_MAX_KP);
@@ -412,6 +430,7 @@ extern "C" int evz_chain_scan(evz_handle* h, const double* G, const int32_t* sta
                               const double* seed_S, const double* seed_G,
                               double* S, double* H_fixed, double* summary, void* stream) {
     if (!h) return EVZ_E_ARG;
+    EVZ_ENTER(h);
     EVZ_REQUIRE(h, G && status, "null pointer");
     EVZ_REQUIRE(h, S || summary, "nothing to compute");
     if (n_pairs <= 0) return EVZ_OK;
@@ -469,6 +488,7 @@ extern "C" int evz_chain_scan(evz_handle* h, const double* G, const int32_t* sta
 extern "C" int evz_chain_seed_apply(evz_handle* h, const double* summaries, int world, int rank, int policy, int n_pairs,
                                     double* S, double* H_fixed, double* seeds_out, void* stream) {
     if (!h) return EVZ_E_ARG;
+    EVZ_ENTER(h);
     EVZ_REQUIRE(h, summaries && S && seeds_out, "null pointer");
     EVZ_REQUIRE(h, world >= 1 && rank >= 0 && rank < world, "rank must be in [0, world)");
     if (n_pairs <= 0) return EVZ_OK;
@@ -489,6 +509,7 @@ extern "C" int evz_remap(evz_handle* h, const double* pts_in, const int32_t* fra
                          const double* S, int n_frames, double sx, double sy, int inverse,
                          double* pts_out, void* stream) {
     if (!h) return EVZ_E_ARG;
+    EVZ_ENTER(h);
     EVZ_REQUIRE(h, pts_in && frame_idx && S && pts_out && n_frames > 0, "null pointer");
     if (n <= 0) return EVZ_OK;
     const int64_t nb = (n + 255) / 256;
@@ -500,6 +521,7 @@ extern "C" int evz_remap(evz_handle* h, const double* pts_in, const int32_t* fra
 extern "C" int evz_max_movement(evz_handle* h, const double* S, int n_frames, int height, int width,
                                 double* out_max, void* stream) {
     if (!h) return EVZ_E_ARG;
+    EVZ_ENTER(h);
     EVZ_REQUIRE(h, S && out_max && n_frames > 0 && height > 0 && width > 0, "bad argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int bx = (height * width + 256 * 8 - 1) / (256 * 8);

@@ -49,6 +49,10 @@ struct evz_handle {
 
 #define EVZ_LAUNCH_CHECK(h) EVZ_CUDA_CHECK(h, cudaGetLastError())
 
+// every entry point runs on the handle's device, whatever device the calling thread had current
+#define EVZ_ENTER(h) do { int d__ = -1; if (cudaGetDevice(&d__) != cudaSuccess || d__ != (h)->device)                     \
+        EVZ_CUDA_CHECK(h, cudaSetDevice((h)->device)); } while (0)
+
 #define EVZ_REQUIRE(h, cond, msg) do { if (!(cond)) { EVZ_SET_ERR(h, "%s: %s", __func__, msg); return EVZ_E_ARG; } } while (0)
 
 // returns a device scratch region of at least `bytes` (256-byte aligned); contents undefined

@@ -308,6 +308,7 @@ extern "C" int evz_ingest(evz_handle* h, const void* raw_desc, int raw_is_f32, i
                           uint8_t* desc, int32_t* ckey, float* coords, int32_t* canon, int32_t* bad_count,
                           void* stream) {
     if (!h) return EVZ_E_ARG;
+    EVZ_ENTER(h);
     EVZ_REQUIRE(h, raw_desc && raw_coords && raw_off && row_off && desc && ckey && coords && canon && bad_count, "null pointer");
     EVZ_REQUIRE(h, d > 0 && d <= EVZ_DESC_BYTES && d % 4 == 0, "descriptor width must be a multiple of 4, at most 128");
     if (n_frames <= 0) return EVZ_OK;
@@ -332,6 +333,7 @@ extern "C" int evz_filter_matches(evz_handle* h, const int32_t* top2_idx, const 
                                   uint8_t* surv, int32_t* m_idx, float* m_pts, int32_t* m_cnt,
                                   int32_t* n_filtered, int32_t* status, void* stream) {
     if (!h) return EVZ_E_ARG;
+    EVZ_ENTER(h);
     EVZ_REQUIRE(h, top2_idx && top2_d2 && coords && canon && row_off && n_kp && pair_q && pair_t && out_off &&
                    m_idx && m_pts && m_cnt && n_filtered && status, "null pointer");
     if (max_kp > evz::kMaxKpSmem) {
@@ -356,6 +358,7 @@ extern "C" int evz_concat_dedup(evz_handle* h, int n_types, const float* const* 
                                 int n_pairs, const int32_t* status, int max_total, const int32_t* out_off,
                                 float* out_pts, int32_t* out_cnt, void* stream) {
     if (!h) return EVZ_E_ARG;
+    EVZ_ENTER(h);
     EVZ_REQUIRE(h, n_types >= 1 && n_types <= EVZ_MAX_TYPES, "n_types must be in [1, EVZ_MAX_TYPES]");
     EVZ_REQUIRE(h, pts && off && cnt && status && out_off && out_pts && out_cnt, "null pointer");
     if (max_total > EVZ_MAX_KP) {

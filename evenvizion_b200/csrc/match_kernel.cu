@@ -110,6 +110,8 @@ struct MatchArgs {
     int dbg;                   // EVZ_OPT_MATCH_DEBUG: 1 = the V-space epilogue releases every accumulator without draining it
     int pair_mode;             // 1: items are (pair, block of 512 query rows) shared by a CTA pair; work item index =
                                //    2 * list index + CTA rank (match_top2_vkernel_t<2>)
+    int n_kb;                  // data K blocks of 32 bytes that hold descriptor bytes: 4 for SIFT (128 B), 1 for ORB (32 B);
+                               //    the rest of the 128-byte row is zero padding and is not multiplied (match_top2_vkernel)
 };
 
 __device__ __forceinline__ Item load_item(const MatchArgs& a, int it) {
@@ -892,6 +894,7 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
             // and a suspended try_wait wakes up late.
             constexpr uint32_t idesc = umma_idesc_u8(128, kBlockT);
             const uint64_t da_e = umma_desc_nosw(smem_u32(a_s), 128, 256);
+            const int n_kb = args.n_kb;
             uint32_t stage = 0, sphase = 0, qi = 0, gs[2] = {0, 0};
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
                 const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
@@ -907,11 +910,20 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
                         const uint32_t aph = gs[sub]++ & 1;
                         mbar_wait_spin(&acc_empty[sub], aph ^ 1);
                         tc_fence_after();
+                        if (n_kb == kRowBytes / 32) {
 #pragma unroll
-                        for (int k = 0; k < kRowBytes / 32; ++k) {
-                            const uint64_t da = umma_desc_sw128(q_addr + sub * (128 * kRowBytes) + k * 32);
-                            const uint64_t db = umma_desc_sw128(t_addr + k * 32);
-                            umma_i8(tmem_base + sub * kBlockT, da, db, idesc, k > 0 ? 1u : 0u);
+                            for (int k = 0; k < kRowBytes / 32; ++k) {
+                                const uint64_t da = umma_desc_sw128(q_addr + sub * (128 * kRowBytes) + k * 32);
+                                const uint64_t db = umma_desc_sw128(t_addr + k * 32);
+                                umma_i8(tmem_base + sub * kBlockT, da, db, idesc, k > 0 ? 1u : 0u);
+                            }
+                        } else {
+                            // short descriptors (ORB: one 32-byte K block): the zero padding is not multiplied
+                            for (int k = 0; k < n_kb; ++k) {
+                                const uint64_t da = umma_desc_sw128(q_addr + sub * (128 * kRowBytes) + k * 32);
+                                const uint64_t db = umma_desc_sw128(t_addr + k * 32);
+                                umma_i8(tmem_base + sub * kBlockT, da, db, idesc, k > 0 ? 1u : 0u);
+                            }
                         }
                         umma_i8(tmem_base + sub * kBlockT, da_e, db_e, idesc, 1u);
                         umma_commit(&acc_full[sub]);
@@ -1514,7 +1526,16 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
                               const int32_t* row_off, const int32_t* n_kp,
                               const int32_t* pair_q, const int32_t* pair_t, const int32_t* out_off, int n_pairs,
                               int32_t* top2_idx, int32_t* top2_d2, void* stream) {
+    return evz_match_top2_d(h, desc, EVZ_DESC_BYTES, ckey, total_rows, row_off, n_kp, pair_q, pair_t, out_off, n_pairs, top2_idx, top2_d2, stream);
+}
+
+extern "C" int evz_match_top2_d(evz_handle* h, const uint8_t* desc, int desc_bytes, const int32_t* ckey, int64_t total_rows,
+                                const int32_t* row_off, const int32_t* n_kp,
+                                const int32_t* pair_q, const int32_t* pair_t, const int32_t* out_off, int n_pairs,
+                                int32_t* top2_idx, int32_t* top2_d2, void* stream) {
     if (!h) return EVZ_E_ARG;
+    EVZ_ENTER(h);
+    EVZ_REQUIRE(h, desc_bytes > 0 && desc_bytes <= EVZ_DESC_BYTES, "desc_bytes must be in [1, 128]");
     EVZ_REQUIRE(h, desc && ckey && row_off && n_kp && pair_q && pair_t && out_off && top2_idx && top2_d2, "null pointer");
     EVZ_REQUIRE(h, total_rows > 0 && total_rows % EVZ_ROW_ALIGN == 0 && total_rows < (int64_t(1) << 31), "total_rows must be a positive multiple of 256 below 2^31");
     EVZ_REQUIRE(h, (reinterpret_cast<uintptr_t>(desc) & 127) == 0 && (reinterpret_cast<uintptr_t>(ckey) & 15) == 0, "desc must be 128-byte and ckey 16-byte aligned");
@@ -1543,7 +1564,7 @@ extern "C" int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t*
     int32_t* n_items = reinterpret_cast<int32_t*>(sb);
     int32_t* items = reinterpret_cast<int32_t*>(sb + 256);
     evz::MatchArgs a{ckey, row_off, n_kp, pair_q, pair_t, out_off, items, n_items, top2_idx, top2_d2, -512, nullptr, nullptr, nullptr, 256u,
-                     nullptr, nullptr, 0, h->opt_match_debug, 0};
+                     nullptr, nullptr, 0, h->opt_match_debug, 0, (desc_bytes + 31) / 32};
 #define EVZ_MATCH_LAUNCH(CH, EW)                                                                                         \
     do {                                                                                                                 \
         using Cfg = evz::MatchCfg<CH, EW>;                                                                               \

@@ -1141,6 +1141,7 @@ extern "C" int evz_find_homography(evz_handle* h, const float* pts, const int32_
                                    int32_t* best_hyp, int32_t* best_cnt, uint8_t* mask_best, double* H_best,
                                    void* stream) {
     if (!h) return EVZ_E_ARG;
+    EVZ_ENTER(h);
     EVZ_REQUIRE(h, pts && off && cnt && status && H, "null pointer");
     EVZ_REQUIRE(h, n_hyp > 0, "n_hyp must be positive");
     EVZ_REQUIRE(h, (reinterpret_cast<uintptr_t>(pts) & 15) == 0, "pts must be 16-byte aligned");

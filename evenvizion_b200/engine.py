@@ -202,8 +202,8 @@ class GeometryEngine:
         rows = st.rows
         top2_idx = self._empty((rows, 2), torch.int32)
         top2_d2 = self._empty((rows, 2), torch.int32)
-        self._check(self.lib.evz_match_top2(self.h, _ptr(st.desc), _ptr(st.ckey), rows, _ptr(st.row_off), _ptr(st.n_kp),
-                                            _ptr(pq), _ptr(pt), _ptr(out_off), P, _ptr(top2_idx), _ptr(top2_d2), self._stream()))
+        self._check(self.lib.evz_match_top2_d(self.h, _ptr(st.desc), int(st.d), _ptr(st.ckey), rows, _ptr(st.row_off), _ptr(st.n_kp),
+                                              _ptr(pq), _ptr(pt), _ptr(out_off), P, _ptr(top2_idx), _ptr(top2_d2), self._stream()))
         surv = self._empty((rows,), torch.uint8)
         m_idx = self._empty((rows, 2), torch.int32)
         m_pts = self._empty((rows, 4), torch.float32)
@@ -348,8 +348,8 @@ class GeometryEngine:
         lib, h, strm = self.lib, self.h, self._stream()
         mk = st.max_kp
         at = lambda t, k=1: C.c_void_p(t.data_ptr() + p0 * k * t.element_size())
-        self._check(lib.evz_match_top2(h, _ptr(st.desc), _ptr(st.ckey), st.rows, _ptr(st.row_off), _ptr(st.n_kp),
-                                       at(r.pair_q), at(r.pair_t), at(r.out_off), n, _ptr(r.top2_idx), _ptr(r.top2_d2), strm))
+        self._check(lib.evz_match_top2_d(h, _ptr(st.desc), int(st.d), _ptr(st.ckey), st.rows, _ptr(st.row_off), _ptr(st.n_kp),
+                                         at(r.pair_q), at(r.pair_t), at(r.out_off), n, _ptr(r.top2_idx), _ptr(r.top2_d2), strm))
         self._check(lib.evz_filter_matches(h, _ptr(r.top2_idx), _ptr(r.top2_d2), _ptr(st.coords), _ptr(st.canon),
                                            _ptr(st.row_off), _ptr(st.n_kp), at(r.pair_q), at(r.pair_t), at(r.out_off), n,
                                            mk, float(ratio), int(min_matching_pts), _ptr(r.surv), _ptr(r.m_idx), _ptr(r.m_pts),

@@ -70,6 +70,10 @@ extern "C" {
 #define EVZ_FLAG_DISP_OVERFLOW 1 /* a displacement was non-finite or > EVZ_R_MAX (reference round() raises) */
 #define EVZ_FLAG_TOO_MANY_POINTS 2 /* cnt[p] > EVZ_MAX_KP although max_cnt promised otherwise: nothing was written */
 
+/* A handle belongs to ONE device and ONE host thread / stream at a time: its grow-only scratch block is shared by all
+ * entry points, so two calls that overlap in time on different streams (or threads) would race on it.  Every entry point
+ * makes the handle's device current (cudaSetDevice) before it launches.  Growing the scratch block synchronises the
+ * device once (cudaDeviceSynchronize + cudaFree + cudaMalloc); steady-state calls do not synchronise. */
 typedef struct evz_handle evz_handle;
 
 int         evz_version(void);
@@ -129,6 +133,14 @@ int evz_match_top2(evz_handle* h, const uint8_t* desc, const int32_t* ckey, int6
                    const int32_t* row_off, const int32_t* n_kp,
                    const int32_t* pair_q, const int32_t* pair_t, const int32_t* out_off, int n_pairs,
                    int32_t* top2_idx, int32_t* top2_d2, void* stream);
+/* The same with the number of descriptor bytes that are in use (the rest of every 128-byte row is zero padding):
+ * 32 for ORB (frame_processing.py:59-61) -- one 32-byte K block is multiplied instead of four.  Results are those of
+ * evz_match_top2 (which is this call with desc_bytes = 128). */
+int evz_match_top2_d(evz_handle* h, const uint8_t* desc, int desc_bytes, const int32_t* ckey, int64_t total_rows,
+                     const int32_t* row_off, const int32_t* n_kp,
+                     const int32_t* pair_q, const int32_t* pair_t, const int32_t* out_off, int n_pairs,
+                     int32_t* top2_idx, int32_t* top2_d2, void* stream);
+
 
 /* ---- K1b/K2: Lowe ratio test + many-to-one filter + coordinate de-dup + gather.  Replaces
  * lowes_ratio_test / filter_corresponding_points (matching.py:166-239), the point gather
@@ -160,9 +172,15 @@ int evz_filter_matches(evz_handle* h, const int32_t* top2_idx, const int32_t* to
  *   n_hyp      hypotheses per pair (counter-based sampler: seed, pair_id_base + p, level)
  *   fail_status value written to status[p] when no model is found (EVZ_ST_NO_MODEL_1/2)
  * outputs (any may be NULL except H and status)
- *   H          DEV double [P][9]  refined homography (normalised DLT + LM), h22 = 1
- *   mask       DEV uint8 [rows]   final inlier mask: f32 reprojection error of H <= thresh^2
- *   inl_cnt    DEV int32 [P]      sum(mask)
+ *   H          DEV double [P][9]  refined homography, h22 = 1: Levenberg-Marquardt on the 8 free parameters over the
+ *                                 winner's inlier set (OpenCV's damping schedule and stop rule), started from the winning
+ *                                 4-point model -- not from a normalised DLT as cv2 does; same optimum (<= 1e-3 px),
+ *                                 first step undamped, stop when a step moves no point by more than 1e-6 px, <= 20 steps
+ *   mask       DEV uint8 [rows]   final inlier mask: f32 reprojection error of the REFINED H <= thresh^2.  This is what
+ *                                 cv2 >= 4.x returns (the oracle is pinned to cv2 4.13); the opencv-contrib 3.4.2 pinned by
+ *                                 the reference's requirements.txt returns the RANSAC consensus mask (= mask_best) instead,
+ *                                 so the 70 % gate can differ for pairs that sit on the boundary
+ *   inl_cnt    DEV int32 [P]      sum(mask): the count the min_inlier_frac gate (utils.py:359) is applied to
  *   best_hyp   DEV int32 [P]      winning hypothesis (max inliers, ties -> lowest index)
  *   best_cnt   DEV int32 [P]      its inlier count
  *   mask_best  DEV uint8 [rows]   its inlier mask (the refit set)

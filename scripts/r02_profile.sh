@@ -1,0 +1,11 @@
+# Round-2 evidence: every command runs plain first (exit 0), then under ncu (B200_PROFILING.md recipe).
+set -x
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu --pairs 2000"
+$CMD > gpurun_out/r02_plain_bench2000.log 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'ransac|static|filter_m|match_|build_|prod_|fill_|fixed_' -s 51 -c 34 --csv --log-file gpurun_out/r02_launches_bench_pairs2000.csv $CMD > gpurun_out/r02_ncu_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'ransac_score' -s 6 -c 2 -o gpurun_out/r02_prof_score $CMD > gpurun_out/r02_ncu_score.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'ransac_refit' -s 6 -c 2 -o gpurun_out/r02_prof_refit $CMD > gpurun_out/r02_ncu_refit.log 2>&1
+CMD2="python scripts/bench_match.py 10000 2048 0"
+$CMD2 > gpurun_out/r02_plain_bench_match10000.log 2>&1 || exit 1
+ncu --set full --clock-control none --import-source on -k regex:'match_top2_vkernel' -s 3 -c 1 -o gpurun_out/r02_prof_vkernel $CMD2 > gpurun_out/r02_ncu_vkernel.log 2>&1
+cat gpurun_out/r02_plain_bench_match10000.log

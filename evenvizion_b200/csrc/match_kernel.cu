@@ -1634,7 +1634,7 @@ extern "C" int evz_match_top2_d(evz_handle* h, const uint8_t* desc, int desc_byt
         }
         EVZ_LAUNCH_CHECK(h);
         if (tev) EVZ_CUDA_CHECK(h, cudaEventRecord(tev[1], st));
-        evz::match_fixup_kernel<<<h->sm_count * 8, 128, 0, st>>>(desc, a);
+        evz::match_fixup_kernel<<<h->sm_count * 16, 128, 0, st>>>(desc, a);      // latency-bound (one row per CTA at a time): fill the SMs
         EVZ_LAUNCH_CHECK(h);
         // pairs whose train frame has a norm range the fifth K block cannot encode: legacy kernel (normally no items)
         a.items = items_slow;

@@ -413,6 +413,41 @@ static void run_sts2(int sms, int nw, long long* d_cycles, const char* name) {
            s / (iters * 8.0 * nw), s / (iters * 8.0));
 }
 
+
+// ------------------------------------------------------------------------------------------------ stg: predicated global stores
+// kMode 0: all lanes, 1: predicate false, 2: lane 0 only, 3: two moving lanes.  Every CTA writes its own 64 KB region (L2 resident).
+template <int kMode>
+__global__ void __launch_bounds__(1024, 1) stg_kernel(int iters, int zero, uint8_t* buf, long long* cycles) {
+    const int lane = threadIdx.x & 31;
+    uint8_t* addr = buf + static_cast<size_t>(blockIdx.x) * 65536 + threadIdx.x * 16;
+    uint32_t a = threadIdx.x, b = a * 3, c = a * 5, d = a * 7;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+        const int on = kMode == 0 ? 1 : kMode == 1 ? zero : kMode == 2 ? ((lane == 0) | zero) : ((lane == (i & 31)) | (lane == ((i * 7 + 3) & 31)) | zero);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p st.global.v4.b32 [%0], {%1,%2,%3,%4};\n\t}"
+                         :: "l"(addr + u * 16384), "r"(a), "r"(b), "r"(c), "r"(d), "r"(on) : "memory");
+        a += i;
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+template <int kMode>
+static void run_stg(int sms, int nw, uint8_t* buf, long long* d_cycles, const char* name) {
+    const int iters = 2000;
+    stg_kernel<kMode><<<sms, nw * 32>>>(iters, 0, buf, d_cycles);
+    cudaDeviceSynchronize();
+    std::vector<long long> h(sms);
+    cudaMemcpy(h.data(), d_cycles, sms * sizeof(long long), cudaMemcpyDeviceToHost);
+    double s = 0; for (int i = 0; i < sms; ++i) s += h[i];
+    s /= sms;
+    printf("stg  warps/SM %2d  %-16s: %.2f clk per STG.128 per SM, %.1f clk per warp per store\n", nw, name, s / (iters * 4.0 * nw), s / (iters * 4.0));
+}
+
 // ================================================================================================ host
 static double avg_cycles(long long* d_cycles, int n) {
     std::vector<long long> h(n);
@@ -507,6 +542,16 @@ int main(int argc, char** argv) {
             run_sts2<8, 2>(sms, nw, d_cycles, "lane 0");
             run_sts2<4, 0>(sms, nw, d_cycles, "all lanes");
             run_sts2<4, 2>(sms, nw, d_cycles, "lane 0");
+        }
+    }
+
+    if (all || !strcmp(what, "stg")) {
+        uint8_t* buf; CK(cudaMalloc(&buf, static_cast<size_t>(sms) * 65536));
+        for (int nw : {8, 16}) {
+            run_stg<0>(sms, nw, buf, d_cycles, "all lanes");
+            run_stg<1>(sms, nw, buf, d_cycles, "pred false");
+            run_stg<2>(sms, nw, buf, d_cycles, "lane 0");
+            run_stg<3>(sms, nw, buf, d_cycles, "2 moving lanes");
         }
     }
     if (all || !strcmp(what, "layout")) {

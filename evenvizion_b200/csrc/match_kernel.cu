@@ -1053,6 +1053,634 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
 }
 
 
+// =====================================================================================================
+// Two-pass V-space kernel (match_top2_wkernel, EVZ_OPT_MATCH_VARIANT = 8; a measured NEGATIVE result of round 2: bit-identical,
+// a quarter of the shared-memory store cycles, and 2.4 x slower than match_top2_vkernel -- pass B is a serial chain of ~15
+// ballot / TMEM load / store steps per tile and warp, ~55 instructions each, with nothing to hide its latencies behind;
+// pass A alone already takes as long as the whole one-pass drain because the accumulator is held until the end).
+// Same TMA / tcgen05 front end, same
+// V = q.t + E_c accumulators, same exact end-of-item resolution and certification as match_top2_vkernel; what
+// changes is how the two best chunks of a row reach shared memory.
+//
+// What bounds match_top2_vkernel (round-2 microbenchmarks, scripts/microbench/mb2.cu): a STS.128 occupies the
+// shared-memory store path for ~4.4 clk per SM as soon as ONE lane is active (1 clk when none is), so the four
+// predicated stores of a chunk cost ~17 clk whenever any of the warp's 32 rows saves -- which, with 32 independent
+// rows per warp, is 62 % of all chunks at 2 048 keypoints: ~1 560 clk of store path per 256-row tile against the
+// 1 500 clk the ten tcgen05.mma of a tile take.  With short descriptors (one K block instead of four) the kernel is
+// only 6 % faster: the drain, i.e. the store path, is the bound.
+//
+// Here the drain of an accumulator row is two passes over tensor memory (reading TMEM is cheap: a drain that only
+// loads runs at the front-end rate):
+//   pass A  (shape 32x32b, thread = row) every 16-column chunk -> its maximum -> chunk key -> sorted top-3 of chunk
+//           keys, exactly as before, but NOTHING is stored and no slot bookkeeping is done per chunk;
+//   after the tile's 16 chunks a row knows which of them (at most two) now belong to its two best chunks;
+//   pass B  only those chunks are read again, with shape 16x256b.x2, in which a QUAD of threads holds one row's 16
+//           columns (4 each): one STS.128 per thread saves the chunk, and one store instruction serves 8 rows.
+//           The (chunk, half-warp) pairs with a saving row come from one redux.or; who saves and into which slot
+//           travels by two ballots.  A chunk that only one row wants costs ~5.5 clk of store path instead of ~17,
+//           chunks nobody wants cost nothing, and the tile's transient records (chunks that were among the row's
+//           best two for a while but not at the end of the tile) are never stored.
+// Slot layout: [slot 2][row 256][part 4] x 16 B; part q of a slot holds columns 2q, 2q+1, 8+2q, 8+2q+1 of the chunk.
+__device__ __forceinline__ void wchunk_key(const uint32_t* r, uint32_t tagc, uint32_t mul, uint32_t& M1, uint32_t& M2, uint32_t& M3) {
+    const uint32_t a = __vimax3_u32(r[0], r[1], r[2]), b = __vimax3_u32(r[3], r[4], r[5]), c = __vimax3_u32(r[6], r[7], r[8]);
+    const uint32_t d = __vimax3_u32(r[9], r[10], r[11]), e = __vimax3_u32(r[12], r[13], r[14]);
+    const uint32_t cm = max(__vimax3_u32(a, b, c), __vimax3_u32(d, e, r[15]));
+    uint32_t cmk;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(cmk) : "r"(cm), "r"(mul), "r"(tagc));
+    const uint32_t t = min(M1, cmk), u = __vimin3_u32(M1, M2, cmk);
+    M1 = max(M1, cmk);
+    M3 = max(M3, u);
+    M2 = max(M2, t);
+}
+
+__global__ void __launch_bounds__(VCfg::threads, 1)
+match_top2_wkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args) {
+    using Cfg = VCfg;
+    static_assert(kVC == 16, "the two-pass kernel saves 16-column chunks");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* q_s = smem + Cfg::q_off;
+    uint8_t* t_s = smem + Cfg::t_off;
+    uint8_t* e_s = smem + Cfg::e_off;
+    uint8_t* a_s = smem + Cfg::a_off;
+    Item* item_s = reinterpret_cast<Item*>(smem + Cfg::item_off);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::bar_off);
+    uint64_t* full = bars;                       // [kStages] train tile + its fifth K block landed (TMA tx)
+    uint64_t* empty = full + kStages;            // [kStages] MMA commit
+    uint64_t* q_full = empty + kStages;          // [2] query block landed + item descriptor published
+    uint64_t* q_empty = q_full + 2;              // [2] MMA commit + 8 epilogue warps
+    uint64_t* acc_full = q_empty + 2;            // [2] accumulator (= query sub-tile) ready (MMA commit)
+    uint64_t* acc_empty = acc_full + 2;          // [2] accumulator drained (4 epilogue warps each)
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + Cfg::tmem_off);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1 + 8);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_s, 512);
+        tmem_relinquish();
+    }
+    if (warp == 3) {
+        // query-side fifth K block: every row = (255 x 30, 1, 0), no-swizzle core-matrix layout
+        for (int i = lane; i < 256; i += 32) {
+            const bool second = (i >> 3) & 1;          // [group 16][k half 2][row 8] x 16 B
+            reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, second ? 0x0001FFFFu : 0xFFFFFFFFu);
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+    const int n_items = *args.n_items;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------- TMA producer (polling waits, single thread)
+        if (lane == 0) {
+            uint32_t stage = 0, sphase = 0, qi = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const Item im = load_item(args, it);
+                const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+                ++qi;
+                mbar_wait_spin(&q_empty[qb], qph ^ 1);
+                item_s[qb] = im;
+                if (im.n_tiles == 0) { mbar_arrive(&q_full[qb]); continue; }
+                mbar_arrive_expect_tx(&q_full[qb], kQBytes + im.n_tiles * 32);
+                tma_load_2d(q_s + qb * kQBytes, &tmap, 0, im.q_row0, &q_full[qb]);
+                bulk_load_1d(smem + Cfg::pb_off + qb * Cfg::pb_bytes, args.pbits + static_cast<size_t>(im.t_row0 >> 8) * 8,
+                             im.n_tiles * 32, &q_full[qb]);
+                const uint8_t* ecode = args.ecode + static_cast<size_t>(im.t_row0 >> 8) * kECodeBytes;
+                for (int n = 0; n < im.n_tiles; ++n) {
+                    if (n + kStages < im.n_tiles) {
+                        tma_prefetch_2d(&tmap, 0, im.t_row0 + (n + kStages) * kBlockT);
+                        bulk_prefetch_1d(ecode + static_cast<size_t>(n + kStages) * kECodeBytes, kECodeBytes);
+                    }
+                    mbar_wait_spin(&empty[stage], sphase ^ 1);
+                    mbar_arrive_expect_tx(&full[stage], kTileBytes + kECodeBytes);
+                    tma_load_2d(t_s + stage * kTileBytes, &tmap, 0, im.t_row0 + n * kBlockT, &full[stage]);
+                    bulk_load_1d(e_s + stage * kECodeBytes, ecode + static_cast<size_t>(n) * kECodeBytes, kECodeBytes, &full[stage]);
+                    if (++stage == kStages) { stage = 0; sphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------- MMA issuer (see match_top2_vkernel)
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_u8(128, kBlockT);
+            const uint64_t da_e = umma_desc_nosw(smem_u32(a_s), 128, 256);
+            const int n_kb = args.n_kb;
+            uint32_t stage = 0, sphase = 0, qi = 0, gs[2] = {0, 0};
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+                ++qi;
+                mbar_wait_spin(&q_full[qb], qph);
+                const int n_tiles = item_s[qb].n_tiles, n_sub = item_s[qb].n_sub;
+                const uint32_t q_addr = smem_u32(q_s + qb * kQBytes);
+                for (int n = 0; n < n_tiles; ++n) {
+                    mbar_wait_spin(&full[stage], sphase);
+                    const uint32_t t_addr = smem_u32(t_s + stage * kTileBytes);
+                    const uint64_t db_e = umma_desc_nosw(smem_u32(e_s + stage * kECodeBytes), 128, 256);
+                    for (int sub = 0; sub < n_sub; ++sub) {
+                        const uint32_t aph = gs[sub]++ & 1;
+                        mbar_wait_spin(&acc_empty[sub], aph ^ 1);
+                        tc_fence_after();
+                        if (n_kb == kRowBytes / 32) {
+#pragma unroll
+                            for (int k = 0; k < kRowBytes / 32; ++k) {
+                                const uint64_t da = umma_desc_sw128(q_addr + sub * (128 * kRowBytes) + k * 32);
+                                const uint64_t db = umma_desc_sw128(t_addr + k * 32);
+                                umma_i8(tmem_base + sub * kBlockT, da, db, idesc, k > 0 ? 1u : 0u);
+                            }
+                        } else {
+                            for (int k = 0; k < n_kb; ++k) {
+                                const uint64_t da = umma_desc_sw128(q_addr + sub * (128 * kRowBytes) + k * 32);
+                                const uint64_t db = umma_desc_sw128(t_addr + k * 32);
+                                umma_i8(tmem_base + sub * kBlockT, da, db, idesc, k > 0 ? 1u : 0u);
+                            }
+                        }
+                        umma_i8(tmem_base + sub * kBlockT, da_e, db_e, idesc, 1u);
+                        umma_commit(&acc_full[sub]);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == kStages) { stage = 0; sphase ^= 1; }
+                }
+                umma_commit(&q_empty[qb]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------- epilogue
+        const int grp = (warp - 4) >> 2;                       // query sub-tile = accumulator
+        const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
+        const int row = grp * 128 + quarter * 32 + lane;       // query row within the block
+        const uint32_t slot_base = smem_u32(smem + Cfg::slot_off);
+        const uint32_t taddr = tmem_base + grp * kBlockT + (static_cast<uint32_t>(quarter * 32) << 16);
+        // pass B: this thread's quad position and the two rows (of either half-warp) it stores for
+        const int q4 = lane & 3, r8 = lane >> 2, hl = lane >> 4;
+        const uint32_t quad_base = slot_base + static_cast<uint32_t>(grp * 128 + quarter * 32 + r8) * 64 + q4 * 16;
+        uint32_t g = 0, qi = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+            ++qi;
+            mbar_wait(&q_full[qb], qph);
+            const Item im = item_s[qb];
+            if (grp < im.n_sub) {
+                const int qkey = __ldg(args.ckey + im.q_row0 + row);
+                // sorted top-3 of chunk keys, the physical slot (0 / 1) that holds the second-best chunk, and the position
+                // (tile * 16 + chunk) of the chunks in the best / second-best slot
+                uint32_t M1 = 0, M2 = 0, M3 = 0, secbit = 1;
+                int Tb = -1, Ts = -1;
+                for (int n = 0; n < im.n_tiles; ++n) {
+                    // keys of earlier tiles beat every key of this tile with the same V (lowest index wins)
+                    M1 |= 255u; M2 |= 255u; M3 |= 255u;
+                    mbar_wait(&acc_full[grp], g & 1);
+                    tc_fence_after();
+                    // ---- pass A: chunk maxima and top-3 of chunk keys, nothing stored
+                    {
+                        uint32_t r[2][32];
+                        tmem_ld_32x32b_x32(taddr, r[0]);
+#pragma unroll
+                        for (int b = 0; b < 8; ++b) {
+                            tmem_ld_wait_dep(r[b & 1]);
+                            if (b + 1 < 8) tmem_ld_32x32b_x32(taddr + (b + 1) * 32, r[(b + 1) & 1]);
+                            wchunk_key(&r[b & 1][0], 254 - 2 * b, args.mul256, M1, M2, M3);
+                            wchunk_key(&r[b & 1][16], 253 - 2 * b, args.mul256, M1, M2, M3);
+                        }
+                    }
+                    // ---- which chunks of this tile are now the row's best / second-best chunk
+                    const bool nb = (M1 & 255u) != 255u, ns = (M2 & 255u) != 255u;
+                    const int jA = nb ? 254 - static_cast<int>(M1 & 255u) : -1, jB = ns ? 254 - static_cast<int>(M2 & 255u) : -1;
+                    const uint32_t tgtA = secbit;                 // a new best chunk replaces the old second-best one ...
+                    if (nb) secbit ^= 1u;                         // ... and the old best chunk becomes the second-best
+                    const uint32_t tgtB = secbit;
+                    Ts = ns ? n * kVCps + jB : (nb ? Tb : Ts);
+                    Tb = nb ? n * kVCps + jA : Tb;
+                    // ---- pass B: (chunk, half-warp) pairs with a saving row
+                    uint32_t U2 = redux_or((nb ? 1u << (2 * jA + hl) : 0u) | (ns ? 1u << (2 * jB + hl) : 0u));
+                    if (args.dbg == 3) U2 = 0;                      // measurement only: pass A alone (results are garbage)
+                    uint32_t s0[8], s1[8];
+                    int bit = U2 ? __ffs(U2) - 1 : -1;
+                    if (bit >= 0) tmem_ld_16x256b_x2(taddr + (bit >> 1) * kVC + (static_cast<uint32_t>((bit & 1) * 16) << 16), s0);
+                    auto save = [&](uint32_t (&cur)[8], uint32_t (&nxt)[8]) {
+                        U2 &= U2 - 1;
+                        const int nbit = U2 ? __ffs(U2) - 1 : -1;
+                        const int j = bit >> 1, h = bit & 1;
+                        const unsigned W = __ballot_sync(0xffffffffu, jA == j || jB == j);
+                        const unsigned Sb = __ballot_sync(0xffffffffu, (jA == j ? tgtA : tgtB) != 0u);
+                        tmem_ld_wait_dep(cur);
+                        if (nbit >= 0) tmem_ld_16x256b_x2(taddr + (nbit >> 1) * kVC + (static_cast<uint32_t>((nbit & 1) * 16) << 16), nxt);
+                        const int ra = 16 * h + r8, rb = ra + 8;
+                        const uint32_t aa = quad_base + (16 * h) * 64 + ((Sb >> ra) & 1u) * Cfg::slot_stride;
+                        const uint32_t ab = quad_base + (16 * h + 8) * 64 + ((Sb >> rb) & 1u) * Cfg::slot_stride;
+                        asm volatile("{\n\t.reg .pred pa, pb;\n\t"
+                                     "setp.ne.u32 pa, %10, 0;\n\t"
+                                     "setp.ne.u32 pb, %11, 0;\n\t"
+                                     "@pa st.shared.v4.b32 [%0], {%2, %3, %6, %7};\n\t"
+                                     "@pb st.shared.v4.b32 [%1], {%4, %5, %8, %9};\n\t}"
+                                     :: "r"(aa), "r"(ab), "r"(cur[0]), "r"(cur[1]), "r"(cur[2]), "r"(cur[3]), "r"(cur[4]), "r"(cur[5]),
+                                        "r"(cur[6]), "r"(cur[7]), "r"((W >> ra) & 1u), "r"((W >> rb) & 1u) : "memory");
+                        bit = nbit;
+                    };
+                    while (bit >= 0) {
+                        save(s0, s1);
+                        if (bit < 0) break;
+                        save(s1, s0);
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[grp]);
+                    ++g;
+                }
+                // the saves of other lanes of this warp (pass B stores for 8 rows at a time) must be visible to the row's owner
+                __syncwarp();
+                // exact evaluation of the two saved chunks (see match_top2_vkernel); word i = 4 q + e of a slot is column
+                // 2q + (e & 1) + 8 (e >> 1) of the chunk
+                const int hm1 = im.pad + 1;
+                const bool best_first = Ts < 0 || Tb < Ts;
+                int k[2 * kVC];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int T = s == 0 ? Tb : Ts;
+                    const uint32_t sa = slot_base + (s == 0 ? (secbit ^ 1u) : secbit) * Cfg::slot_stride + row * 64;
+                    if (T >= 0) {
+                        const int base = (T >> kVClog) * kBlockT + (T & (kVCps - 1)) * kVC;
+                        const int cs = (2 * hm1) * 256 + ((s == 0) == best_first ? 0 : kVC);
+                        uint32_t ps;                       // norm parity of the chunk's columns, moved to bits 8..
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ps) : "r"(smem_u32(smem + Cfg::pb_off) + qb * Cfg::pb_bytes + (base >> 3)));
+                        ps <<= 8;
+#pragma unroll
+                        for (int part = 0; part < 4; ++part) {
+                            const int4 v = lds128(sa + part * 16);
+                            const int c0 = 2 * part, c1 = 2 * part + 1, c2 = 8 + 2 * part, c3 = 9 + 2 * part;
+                            k[s * kVC + part * 4 + 0] = mad_key(v.x, args.neg512, cs) + (((ps >> c0) & 256) + c0);
+                            k[s * kVC + part * 4 + 1] = mad_key(v.y, args.neg512, cs) + (((ps >> c1) & 256) + c1);
+                            k[s * kVC + part * 4 + 2] = mad_key(v.z, args.neg512, cs) + (((ps >> c2) & 256) + c2);
+                            k[s * kVC + part * 4 + 3] = mad_key(v.w, args.neg512, cs) + (((ps >> c3) & 256) + c3);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kVC; ++i) k[s * kVC + i] = INT_MAX;
+                    }
+                }
+                int m1 = INT_MAX, m2 = INT_MAX;
+#pragma unroll
+                for (int i = 0; i < kVC; ++i) top2_pair(k[2 * i], k[2 * i + 1], m1, m2);
+                const int base_b = Tb >= 0 ? (Tb >> kVClog) * kBlockT + (Tb & (kVCps - 1)) * kVC : 0;
+                const int base_s = Ts >= 0 ? (Ts >> kVClog) * kBlockT + (Ts & (kVCps - 1)) * kVC : 0;
+                const int base_lo = best_first ? base_b : base_s, base_hi = best_first ? base_s : base_b;
+                const int c1 = ((m1 & kVC) ? base_hi : base_lo) + (m1 & (kVC - 1)), c2 = ((m2 & kVC) ? base_hi : base_lo) + (m2 & (kVC - 1));
+                const int I1 = (m1 != INT_MAX && c1 < im.nt) ? c1 : -1, I2 = (m2 != INT_MAX && c2 < im.nt) ? c2 : -1;
+                const int V1 = m1 >> 8, V2 = m2 >> 8;
+                // every column outside the two slots has V <= V3, i.e. ||t||^2 - 2 q.t >= 2 (hmax + 1 - V3)
+                const bool third = M3 > 255u;
+                const int bound = 2 * (hm1 - static_cast<int>(M3 >> 8));
+                const bool flagged = third && (I2 < 0 || V2 >= bound);
+                if (row < im.nq_left) {
+                    const int qn = qkey >> 8;
+                    const int64_t o_row = static_cast<int64_t>(im.out_row0) + row;
+                    int2 oi, od;
+                    oi.x = flagged ? kFlagged : I1; od.x = I1 >= 0 ? V1 + qn : -1;
+                    oi.y = I2;                      od.y = I2 >= 0 ? V2 + qn : -1;
+                    reinterpret_cast<int2*>(args.top2_idx)[o_row] = oi;
+                    reinterpret_cast<int2*>(args.top2_d2)[o_row] = od;
+                    if (flagged) {
+                        const int pos = atomicAdd(args.fix_count, 1);
+                        if (pos < args.fix_capacity) args.fix_list[pos] = it * 256 + row;
+                    }
+                }
+                // the slots are rewritten by the next item's pass B (any lane of the warp): every row must have read its own first
+                __syncwarp();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_empty[qb]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+
+// =====================================================================================================
+// Sixteen-warp V-space kernel (match_top2_xkernel, EVZ_OPT_MATCH_VARIANT = 9; a measured NEGATIVE result of round 2:
+// bit-identical, 19 % slower than match_top2_vkernel at 2 048 keypoints and 14 % at 8 192; the two-stage ring alone costs
+// the front end 15 % (0.80 vs 0.70 ms per 2 000 pairs), and with setmaxnreg (EVZ_X_SETMAXNREG: 40 / 112 registers) the
+// kernel hung on B200 -- it runs at the 96 registers of its launch bounds).  Same algorithm as match_top2_vkernel;
+// every accumulator is drained by EIGHT warps instead of four: warp = (accumulator, column half, TMEM lane quarter),
+// thread = one query row x 128 of the 256 columns of a tile.  Why: a warp reads tensor memory at ~61 B/clk
+// (profiles/r01b_tmem_read_microbench.txt: 244 B/clk/SM with 4 warps, ~390 with 8), so four warps need >= 540 clk to pull
+// a 128 KB accumulator through their registers -- with the max tree interleaved one batch behind the loads the drain
+// takes ~900 clk against the 750 clk the five tcgen05.mma of the other accumulator take, and nothing else in the SM
+// hides it (one drain warp per scheduler and accumulator).  Eight warps halve that and give every scheduler two
+// independent drains of the same accumulator.
+// The price is shared memory: each (row, column half) keeps its own two save slots (64 KB instead of 32), paid for with
+// a two-stage train-tile ring (a stage is released 1 500 clk before it is needed again; the TMA round trip is shorter).
+// At the end of an item both halves resolve their own exact top-2 (each certified against its own third chunk
+// maximum) and half 1 hands its result to half 0 through shared memory (named barrier per lane quarter), which
+// merges the four candidates and writes the row.  Registers: 640 threads leave 96 per thread at launch; the four
+// control warps give theirs back (setmaxnreg.dec 40) and the sixteen drain warps take 112.
+struct XCfg {
+    static constexpr int threads   = 128 + 512;
+    static constexpr int stages    = 2;
+    static constexpr int q_off     = 0;                                       // 2 x 32 KB
+    static constexpr int t_off     = q_off + 2 * kQBytes;                     // stages x 32 KB
+    static constexpr int e_off     = t_off + stages * kTileBytes;             // stages x 8 KB
+    static constexpr int a_off     = e_off + stages * kECodeBytes;            // 4 KB
+    static constexpr int slot_off  = a_off + 128 * 32;                        // [half 2][slot 2][part 4][row 256] x 16 B
+    static constexpr int part_stride = 256 * 16;
+    static constexpr int slot_stride = 4 * part_stride;
+    static constexpr int half_stride = 2 * slot_stride;
+    static constexpr int pb_bytes  = (EVZ_MAX_KP / kBlockT) * 32;
+    static constexpr int pb_off    = slot_off + 2 * half_stride;              // 2 x pb_bytes
+    static constexpr int merge_off = pb_off + 2 * pb_bytes;                   // 2 x [row 256] x (int4 + flag)
+    static constexpr int merge_bytes = 256 * 20;
+    static constexpr int item_off  = merge_off + 2 * merge_bytes;
+    static constexpr int bar_off   = item_off + 2 * static_cast<int>(sizeof(Item));
+    static constexpr int n_bars    = 2 * stages + 2 + 2 + 2 + 2;
+    static constexpr int tmem_off  = bar_off + n_bars * 8;
+    static constexpr int total     = tmem_off + 16;
+    static constexpr int smem_bytes = total + 1024;
+    static_assert(smem_bytes <= 227 * 1024, "sixteen-warp match kernel shared memory exceeds 227 KB");
+};
+
+__global__ void __launch_bounds__(XCfg::threads, 1)
+match_top2_xkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs args) {
+    using Cfg = XCfg;
+    constexpr int kSt = Cfg::stages;
+    static_assert(kVC == 16, "one TMEM load per chunk");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* q_s = smem + Cfg::q_off;
+    uint8_t* t_s = smem + Cfg::t_off;
+    uint8_t* e_s = smem + Cfg::e_off;
+    uint8_t* a_s = smem + Cfg::a_off;
+    Item* item_s = reinterpret_cast<Item*>(smem + Cfg::item_off);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::bar_off);
+    uint64_t* full = bars;                       // [kSt] train tile + its fifth K block landed (TMA tx)
+    uint64_t* empty = full + kSt;                // [kSt] MMA commit
+    uint64_t* q_full = empty + kSt;              // [2] query block landed + item descriptor published
+    uint64_t* q_empty = q_full + 2;              // [2] MMA commit + 16 epilogue warps
+    uint64_t* acc_full = q_empty + 2;            // [2] accumulator (= query sub-tile) ready (MMA commit)
+    uint64_t* acc_empty = acc_full + 2;          // [2] accumulator drained (its 8 epilogue warps)
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + Cfg::tmem_off);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int i = 0; i < kSt; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1 + 16);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_ptr_s, 512);
+        tmem_relinquish();
+    }
+    if (warp == 3) {
+        for (int i = lane; i < 256; i += 32) {
+            const bool second = (i >> 3) & 1;          // [group 16][k half 2][row 8] x 16 B
+            reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, second ? 0x0001FFFFu : 0xFFFFFFFFu);
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+    const int n_items = *args.n_items;
+
+    if (warp < 4) {
+#ifdef EVZ_X_SETMAXNREG
+        setmaxnreg_dec<40>();
+#endif
+        if (warp == 0) {
+            // ------------------------------------------------------------- TMA producer (polling waits, single thread)
+            if (lane == 0) {
+                uint32_t stage = 0, sphase = 0, qi = 0;
+                for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                    const Item im = load_item(args, it);
+                    const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+                    ++qi;
+                    mbar_wait_spin(&q_empty[qb], qph ^ 1);
+                    item_s[qb] = im;
+                    if (im.n_tiles == 0) { mbar_arrive(&q_full[qb]); continue; }
+                    mbar_arrive_expect_tx(&q_full[qb], kQBytes + im.n_tiles * 32);
+                    tma_load_2d(q_s + qb * kQBytes, &tmap, 0, im.q_row0, &q_full[qb]);
+                    bulk_load_1d(smem + Cfg::pb_off + qb * Cfg::pb_bytes, args.pbits + static_cast<size_t>(im.t_row0 >> 8) * 8,
+                                 im.n_tiles * 32, &q_full[qb]);
+                    const uint8_t* ecode = args.ecode + static_cast<size_t>(im.t_row0 >> 8) * kECodeBytes;
+                    for (int n = 0; n < im.n_tiles; ++n) {
+                        if (n + kSt < im.n_tiles) {
+                            tma_prefetch_2d(&tmap, 0, im.t_row0 + (n + kSt) * kBlockT);
+                            bulk_prefetch_1d(ecode + static_cast<size_t>(n + kSt) * kECodeBytes, kECodeBytes);
+                        }
+                        mbar_wait_spin(&empty[stage], sphase ^ 1);
+                        mbar_arrive_expect_tx(&full[stage], kTileBytes + kECodeBytes);
+                        tma_load_2d(t_s + stage * kTileBytes, &tmap, 0, im.t_row0 + n * kBlockT, &full[stage]);
+                        bulk_load_1d(e_s + stage * kECodeBytes, ecode + static_cast<size_t>(n) * kECodeBytes, kECodeBytes, &full[stage]);
+                        if (++stage == kSt) { stage = 0; sphase ^= 1; }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ------------------------------------------------------------- MMA issuer (see match_top2_vkernel)
+            if (lane == 0) {
+                constexpr uint32_t idesc = umma_idesc_u8(128, kBlockT);
+                const uint64_t da_e = umma_desc_nosw(smem_u32(a_s), 128, 256);
+                const int n_kb = args.n_kb;
+                uint32_t stage = 0, sphase = 0, qi = 0, gs[2] = {0, 0};
+                for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                    const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+                    ++qi;
+                    mbar_wait_spin(&q_full[qb], qph);
+                    const int n_tiles = item_s[qb].n_tiles, n_sub = item_s[qb].n_sub;
+                    const uint32_t q_addr = smem_u32(q_s + qb * kQBytes);
+                    for (int n = 0; n < n_tiles; ++n) {
+                        mbar_wait_spin(&full[stage], sphase);
+                        const uint32_t t_addr = smem_u32(t_s + stage * kTileBytes);
+                        const uint64_t db_e = umma_desc_nosw(smem_u32(e_s + stage * kECodeBytes), 128, 256);
+                        for (int sub = 0; sub < n_sub; ++sub) {
+                            const uint32_t aph = gs[sub]++ & 1;
+                            mbar_wait_spin(&acc_empty[sub], aph ^ 1);
+                            tc_fence_after();
+                            if (n_kb == kRowBytes / 32) {
+#pragma unroll
+                                for (int k = 0; k < kRowBytes / 32; ++k) {
+                                    const uint64_t da = umma_desc_sw128(q_addr + sub * (128 * kRowBytes) + k * 32);
+                                    const uint64_t db = umma_desc_sw128(t_addr + k * 32);
+                                    umma_i8(tmem_base + sub * kBlockT, da, db, idesc, k > 0 ? 1u : 0u);
+                                }
+                            } else {
+                                for (int k = 0; k < n_kb; ++k) {
+                                    const uint64_t da = umma_desc_sw128(q_addr + sub * (128 * kRowBytes) + k * 32);
+                                    const uint64_t db = umma_desc_sw128(t_addr + k * 32);
+                                    umma_i8(tmem_base + sub * kBlockT, da, db, idesc, k > 0 ? 1u : 0u);
+                                }
+                            }
+                            umma_i8(tmem_base + sub * kBlockT, da_e, db_e, idesc, 1u);
+                            umma_commit(&acc_full[sub]);
+                        }
+                        umma_commit(&empty[stage]);
+                        if (++stage == kSt) { stage = 0; sphase ^= 1; }
+                    }
+                    umma_commit(&q_empty[qb]);
+                }
+            }
+        }
+    } else {
+#ifdef EVZ_X_SETMAXNREG
+        setmaxnreg_inc<112>();
+#endif
+        // ------------------------------------------------------------- epilogue
+        const int e = warp - 4;
+        const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
+        const int grp = (e >> 2) & 1;                          // query sub-tile = accumulator
+        const int half = e >> 3;                               // column half of every tile
+        const int row = grp * 128 + quarter * 32 + lane;       // query row within the block
+        const uint32_t slot_a = smem_u32(smem + Cfg::slot_off) + half * Cfg::half_stride + row * 16, slot_b = slot_a + Cfg::slot_stride;
+        const uint32_t sum = slot_a + slot_b;
+        const uint32_t taddr = tmem_base + grp * kBlockT + half * (kBlockT / 2) + (static_cast<uint32_t>(quarter * 32) << 16);
+        const uint32_t acc_empty_a = smem_u32(&acc_empty[grp]);
+        const uint32_t bar_id = 1 + grp * 4 + quarter;         // the two warps that share this thread's rows
+        constexpr int kCh = kVCps / 2;                         // chunks of this thread per tile
+        uint32_t g = 0, qi = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+            ++qi;
+            mbar_wait(&q_full[qb], qph);
+            const Item im = item_s[qb];
+            if (grp < im.n_sub) {
+                uint32_t M1 = 0, M2 = 0, M3 = 0, sec = slot_b;
+                int Tb = -1, Ts = -1;
+                for (int n = 0; n < im.n_tiles; ++n) {
+                    M1 |= 255u; M2 |= 255u; M3 |= 255u;
+                    const uint32_t o1 = M1, o2 = M2;
+                    mbar_wait(&acc_full[grp], g & 1);
+                    tc_fence_after();
+                    if (args.dbg == 1) {                 // measurement of the TMA / MMA front end alone: results are garbage
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(acc_empty_a) : "memory");
+                        ++g;
+                        continue;
+                    }
+                    {
+                        // eight loads of one chunk each, two ahead of the chunk being processed (four 16-register buffers)
+                        uint32_t r[4][16];
+                        tmem_ld_32x32b_x16(taddr, r[0]);
+                        tmem_ld_32x32b_x16(taddr + 16, r[1]);
+#pragma unroll
+                        for (int c = 0; c < kCh; ++c) {
+                            tmem_ld_wait_dep(r[c & 3]);
+                            if (c + 2 < kCh) {
+                                tmem_ld_32x32b_x16(taddr + (c + 2) * 16, r[(c + 2) & 3]);
+                            } else if (c + 2 == kCh) {
+                                tc_fence_before();
+                                __syncwarp();
+                                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(acc_empty_a) : "memory");
+                            }
+                            vchunk<Cfg::part_stride>(&r[c & 3][0], 254 - half * kCh - c, args.mul256, M1, M2, M3, sec, sum);
+                            keep_alive16(&r[c & 3][0]);
+                        }
+                    }
+                    ++g;
+                    const int nTb = M1 == o1 ? Tb : n * kVCps + 254 - static_cast<int>(M1 & 255u);
+                    Ts = (M1 != o1 && M2 == o1) ? Tb : (M2 == o2 ? Ts : n * kVCps + 254 - static_cast<int>(M2 & 255u));
+                    Tb = nTb;
+                }
+                // exact evaluation of this half's two saved chunks (see match_top2_vkernel)
+                const int hm1 = im.pad + 1;
+                const bool best_first = Ts < 0 || Tb < Ts;
+                int k[2 * kVC];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int T = s == 0 ? Tb : Ts;
+                    const uint32_t sa = s == 0 ? sum - sec : sec;
+                    if (T >= 0) {
+                        const int base = (T >> kVClog) * kBlockT + (T & (kVCps - 1)) * kVC;
+                        const int cs = (2 * hm1) * 256 + ((s == 0) == best_first ? 0 : kVC);
+                        uint32_t ps;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(ps) : "r"(smem_u32(smem + Cfg::pb_off) + qb * Cfg::pb_bytes + (base >> 3)));
+                        ps <<= 8;
+#pragma unroll
+                        for (int part = 0; part < kVC / 4; ++part) {
+                            const int4 v = lds128(sa + part * Cfg::part_stride);
+                            k[s * kVC + part * 4 + 0] = mad_key(v.x, args.neg512, cs) + (((ps >> (part * 4 + 0)) & 256) + part * 4 + 0);
+                            k[s * kVC + part * 4 + 1] = mad_key(v.y, args.neg512, cs) + (((ps >> (part * 4 + 1)) & 256) + part * 4 + 1);
+                            k[s * kVC + part * 4 + 2] = mad_key(v.z, args.neg512, cs) + (((ps >> (part * 4 + 2)) & 256) + part * 4 + 2);
+                            k[s * kVC + part * 4 + 3] = mad_key(v.w, args.neg512, cs) + (((ps >> (part * 4 + 3)) & 256) + part * 4 + 3);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kVC; ++i) k[s * kVC + i] = INT_MAX;
+                    }
+                }
+                int m1 = INT_MAX, m2 = INT_MAX;
+#pragma unroll
+                for (int i = 0; i < kVC; ++i) top2_pair(k[2 * i], k[2 * i + 1], m1, m2);
+                const int base_b = Tb >= 0 ? (Tb >> kVClog) * kBlockT + (Tb & (kVCps - 1)) * kVC : 0;
+                const int base_s = Ts >= 0 ? (Ts >> kVClog) * kBlockT + (Ts & (kVCps - 1)) * kVC : 0;
+                const int base_lo = best_first ? base_b : base_s, base_hi = best_first ? base_s : base_b;
+                const int c1 = ((m1 & kVC) ? base_hi : base_lo) + (m1 & (kVC - 1)), c2 = ((m2 & kVC) ? base_hi : base_lo) + (m2 & (kVC - 1));
+                int I1 = (m1 != INT_MAX && c1 < im.nt) ? c1 : -1, I2 = (m2 != INT_MAX && c2 < im.nt) ? c2 : -1;
+                int V1 = I1 >= 0 ? (m1 >> 8) : kAbsent, V2 = I2 >= 0 ? (m2 >> 8) : kAbsent;
+                // every column of this half outside its two slots has V <= V3, i.e. ||t||^2 - 2 q.t >= 2 (hmax + 1 - V3):
+                // this half's top-2 is exact unless its second distance reaches that bound
+                const bool third = M3 > 255u;
+                const int bound = 2 * (hm1 - static_cast<int>(M3 >> 8));
+                bool flagged = third && (I2 < 0 || V2 >= bound);
+                // merge the halves: the row's two nearest neighbours are among the two of either half
+                int4* mbuf = reinterpret_cast<int4*>(smem + Cfg::merge_off + (qi & 1) * Cfg::merge_bytes);
+                uint32_t* mflag = reinterpret_cast<uint32_t*>(mbuf + 256);
+                if (half == 1) {
+                    mbuf[row] = make_int4(V1, I1, V2, I2);
+                    mflag[row] = flagged ? 1u : 0u;
+                    named_bar_arrive(bar_id, 64);
+                } else {
+                    named_bar_sync(bar_id, 64);
+                    const int4 o = mbuf[row];
+                    flagged = flagged || mflag[row] != 0u;
+                    if (o.y >= 0) top2_insert(o.x, o.y, V1, I1, V2, I2);
+                    if (o.w >= 0) top2_insert(o.z, o.w, V1, I1, V2, I2);
+                    if (row < im.nq_left) {
+                        const int qn = __ldg(args.ckey + im.q_row0 + row) >> 8;
+                        const int64_t o_row = static_cast<int64_t>(im.out_row0) + row;
+                        int2 oi, od;
+                        oi.x = flagged ? kFlagged : I1; od.x = I1 >= 0 ? V1 + qn : -1;
+                        oi.y = I2;                      od.y = I2 >= 0 ? V2 + qn : -1;
+                        reinterpret_cast<int2*>(args.top2_idx)[o_row] = oi;
+                        reinterpret_cast<int2*>(args.top2_d2)[o_row] = od;
+                        if (flagged) {
+                            const int pos = atomicAdd(args.fix_count, 1);
+                            if (pos < args.fix_capacity) args.fix_list[pos] = it * 256 + row;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_empty[qb]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+
 // ---- CTA-pair template (EVZ_OPT_MATCH_VARIANT = 7).  Only kCtas = 2 is instantiated; the kCtas == 1 branches are the
 // default kernel's code path (they are how the 4 % of the note above were measured) and compile to nothing.
 // one accumulator row (256 columns) in 16 loads of one chunk (16 columns) each, two loads ahead of the chunk being
@@ -1550,7 +2178,7 @@ extern "C" int evz_match_top2_d(evz_handle* h, const uint8_t* desc, int desc_byt
     // per-element top-2, 2 = chunk minima of 16, 5 (and any other value) = chunk minima of 8
     const int variant = h->opt_match_variant;
     const bool vpair = variant == 7;                 // V-space kernel on CTA pairs (cta_group::2)
-    const bool vspace = variant == 0 || vpair;
+    const bool vspace = variant == 0 || vpair || variant == 8 || variant == 9;
     // scratch: [counters 256 B][items A][items B][pair_hmax][pair_flag][ecode]
     const size_t items_bytes = evz_align_up(capacity * 8, 256), pair_bytes = evz_align_up(static_cast<size_t>(n_pairs) * 4, 256);
     const size_t fix_bytes = evz_align_up(capacity * 256 * 4, 256);          // every row of every item, at worst
@@ -1601,6 +2229,8 @@ extern "C" int evz_match_top2_d(evz_handle* h, const uint8_t* desc, int desc_byt
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfgT<2>::smem_bytes));
+            EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_wkernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
+            EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_xkernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::XCfg::smem_bytes));
             h->attr_match |= 8u;
         }
         cudaEvent_t* tev = nullptr;
@@ -1625,6 +2255,10 @@ extern "C" int evz_match_top2_d(evz_handle* h, const uint8_t* desc, int desc_byt
             cfg.attrs = at;
             cfg.numAttrs = 1;
             EVZ_CUDA_CHECK(h, cudaLaunchKernelEx(&cfg, evz::match_top2_vkernel_t<2>, h->tmap, h->tmap_half, a));
+        } else if (variant == 9) {
+            evz::match_top2_xkernel<<<h->sm_count, evz::XCfg::threads, evz::XCfg::smem_bytes, st>>>(h->tmap, a);
+        } else if (variant == 8) {
+            evz::match_top2_wkernel<<<h->sm_count, evz::VCfg::threads, evz::VCfg::smem_bytes, st>>>(h->tmap, a);
         } else if (h->opt_match_debug == 1) {
             evz::match_top2_vkernel<1><<<h->sm_count, evz::VCfg::threads, evz::VCfg::smem_bytes, st>>>(h->tmap, a);
         } else if (h->opt_match_debug == 2) {

@@ -90,7 +90,13 @@ int         evz_sm_count(const evz_handle* h);
                                      best chunk, 1 exact top-2 per element, 2 chunk-16 minima;
                                      7: the V-space kernel on CTA pairs (tcgen05 cta_group::2: a 2-CTA cluster shares every
                                      train tile, each CTA stages half of it and drains its own 256 query rows) -- bit-identical,
-                                     5 % slower than 0 on B200, kept for A/B */
+                                     5 % slower than 0 on B200, kept for A/B;
+                                     8: two-pass drain (chunk maxima first, then only the row's two best chunks of the tile are
+                                     re-read from tensor memory in the 16x256b shape and saved by a quad of threads): a quarter of
+                                     the shared-memory store cycles, but 2.4x slower -- the second pass is a serial chain of
+                                     ballot / load / store steps per warp; 9: sixteen drain warps (eight per accumulator, column
+                                     halves, per-half save slots, two-stage tile ring): 19 % slower.  Both bit-identical, kept as
+                                     measured negative results */
 #define EVZ_OPT_RANSAC_NO_PRUNE 3  /* 1: score every valid hypothesis even after one of them counted all matches as inliers
                                      (default 0: hypotheses that can no longer win the (count desc, index asc) arg-max are skipped) */
 #define EVZ_OPT_TIME_MATCH     4  /* 1: evz_match_top2 brackets its main kernel with CUDA events on the caller's stream (a ring of

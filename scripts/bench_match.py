@@ -29,7 +29,7 @@ for v in variants:
     e1.record(); e1.synchronize()
     ms = e0.elapsed_time(e1) / 5
     line = f"variant {v}: {ms:.3f} ms  {2.0*N*N*D*P/ms/1e9:.1f} TOP/s (whole call)"
-    if v in (0, 7):       # V-space kernels: duration of the main kernel alone (EVZ_OPT_TIME_MATCH)
+    if v in (0, 7, 8, 9): # V-space kernels: duration of the main kernel alone (EVZ_OPT_TIME_MATCH)
         eng.set_option(4, 1)
         for _ in range(5): call()
         torch.cuda.synchronize()

@@ -448,6 +448,92 @@ static void run_stg(int sms, int nw, uint8_t* buf, long long* d_cycles, const ch
     printf("stg  warps/SM %2d  %-16s: %.2f clk per STG.128 per SM, %.1f clk per warp per store\n", nw, name, s / (iters * 4.0 * nw), s / (iters * 4.0));
 }
 
+
+// ------------------------------------------------------------------------------------------------ ld16: register layout of tcgen05.ld.16x256b.x2
+// TMEM is filled with value = lane * 1000 + column (tcgen05.st.32x32b); every warp then reads columns [32, 48) of its lane
+// quarter with two 16x256b.x2 loads (lanes +0 and +16) and dumps the eight registers of every thread.
+__global__ void __launch_bounds__(128, 1) ld16_kernel(uint32_t* out) {
+    __shared__ uint32_t tmem_ptr;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_ptr)), "r"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_ptr;
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    for (int b = 0; b < 2; ++b) {
+        uint32_t r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = threadIdx.x * 1000 + b * 32 + j;
+        const uint32_t addr = tmem + b * 32 + lane_addr;
+        TMEM_ST32(addr, r);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    for (int h = 0; h < 2; ++h) {
+        uint32_t r[8];
+        const uint32_t addr = tmem + 32 + (static_cast<uint32_t>(warp * 32 + 16 * h) << 16);
+        asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(addr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[(threadIdx.x * 2 + h) * 8 + j] = r[j];
+    }
+    (void)lane;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(64) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ sts3: quad-shaped predicates, vote / redux cost
+// kMode 0: lanes 0-3 store; 1: lanes 0-3 and 20-23; 2: lanes 0-7; 3: no store, one vote.ballot + one redux.or per iteration
+template <int kMode>
+__global__ void __launch_bounds__(1024, 1) sts3_kernel(int iters, int zero, long long* cycles, uint32_t* sink) {
+    extern __shared__ uint8_t smem[];
+    const int lane = threadIdx.x & 31;
+    const uint32_t addr = smem_u32(smem) + threadIdx.x * 16;
+    uint32_t a = threadIdx.x, b = a * 3, c = a * 5, d = a * 7, acc = 0;
+    const int on = kMode == 0 ? ((lane < 4) | zero) : kMode == 1 ? ((lane < 4) | (lane >= 20 && lane < 24) | zero) : kMode == 2 ? ((lane < 8) | zero) : zero;
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (kMode == 3) {
+                const unsigned bal = __ballot_sync(0xffffffff, (a + u) & 1);
+                unsigned red;
+                asm volatile("redux.sync.or.b32 %0, %1, 0xffffffff;" : "=r"(red) : "r"(a ^ bal));
+                acc += red; a += red & 3;
+            } else {
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %5, 0;\n\t@p st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n\t}"
+                             :: "r"(addr + (u & 3) * 16384), "r"(a), "r"(b), "r"(c), "r"(d), "r"(on) : "memory");
+            }
+        }
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+template <int kMode>
+static void run_sts3(int sms, int nw, long long* d_cycles, uint32_t* d_sink, const char* name) {
+    const int iters = 2000;
+    cudaFuncSetAttribute(sts3_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 4 * 16384);
+    sts3_kernel<kMode><<<sms, nw * 32, 65536 + 4 * 16384>>>(iters, 0, d_cycles, d_sink);
+    cudaDeviceSynchronize();
+    std::vector<long long> h(sms);
+    cudaMemcpy(h.data(), d_cycles, sms * sizeof(long long), cudaMemcpyDeviceToHost);
+    double s = 0; for (int i = 0; i < sms; ++i) s += h[i];
+    s /= sms;
+    printf("sts3 warps/SM %2d  %-34s: %.2f clk per instruction per SM, %.1f clk per warp\n", nw, name, s / (iters * 8.0 * nw), s / (iters * 8.0));
+}
+
 // ================================================================================================ host
 static double avg_cycles(long long* d_cycles, int n) {
     std::vector<long long> h(n);
@@ -552,6 +638,27 @@ int main(int argc, char** argv) {
             run_stg<1>(sms, nw, buf, d_cycles, "pred false");
             run_stg<2>(sms, nw, buf, d_cycles, "lane 0");
             run_stg<3>(sms, nw, buf, d_cycles, "2 moving lanes");
+        }
+    }
+
+    if (all || !strcmp(what, "ld16")) {
+        uint32_t* d_out; CK(cudaMalloc(&d_out, 128 * 2 * 8 * 4));
+        ld16_kernel<<<1, 128>>>(d_out);
+        CK(cudaDeviceSynchronize());
+        std::vector<uint32_t> o(128 * 16);
+        CK(cudaMemcpy(o.data(), d_out, o.size() * 4, cudaMemcpyDeviceToHost));
+        for (int t : {0, 1, 2, 3, 4, 5, 31, 32, 33, 100}) for (int h = 0; h < 2; ++h) {
+            printf("ld16 thread %3d half %d:", t, h);
+            for (int j = 0; j < 8; ++j) printf("  (lane %3u col %2u)", o[(t * 2 + h) * 8 + j] / 1000, o[(t * 2 + h) * 8 + j] % 1000);
+            printf("\n");
+        }
+    }
+    if (all || !strcmp(what, "sts3")) {
+        for (int nw : {8, 16}) {
+            run_sts3<0>(sms, nw, d_cycles, d_sink, "STS.128 lanes 0-3");
+            run_sts3<1>(sms, nw, d_cycles, d_sink, "STS.128 lanes 0-3 + 20-23");
+            run_sts3<2>(sms, nw, d_cycles, d_sink, "STS.128 lanes 0-7");
+            run_sts3<3>(sms, nw, d_cycles, d_sink, "vote.ballot + redux.or (pair)");
         }
     }
     if (all || !strcmp(what, "layout")) {

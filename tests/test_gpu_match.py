@@ -161,12 +161,12 @@ def test_match_epilogue_variants_agree(engine):
     d[4, :] = d[4, 0:1]                   # a whole frame of identical descriptors
     st = engine.ingest(d, ch["coords"])
     outs = {}
-    for v in (0, 1, 2, 5, 7):
+    for v in (0, 1, 2, 5, 7, 8, 9):
         engine.set_option(2, v)
         outs[v] = engine.match(st, list(range(1, 6)), list(range(0, 5)))
     engine.set_option(2, 0)
     q0 = int(st.row_off_h[1])
-    for v in (1, 2, 5, 7):
+    for v in (1, 2, 5, 7, 8, 9):
         assert torch.equal(outs[0].top2_idx[q0:], outs[v].top2_idx[q0:]), v
         assert torch.equal(outs[0].top2_d2[q0:], outs[v].top2_d2[q0:]), v
     # and both equal the oracle on the tie-heavy pairs
@@ -180,7 +180,7 @@ def test_match_epilogue_variants_agree(engine):
 
 def _check_launch_against_gemm(engine, st, pq, pt, counts, dd, offs):
     outs = {}
-    for v in (0, 1, 2, 5, 7):
+    for v in (0, 1, 2, 5, 7, 8, 9):
         engine.set_option(2, v)
         outs[v] = [engine.match(st, pq, pt) for _ in range(2 if v == 0 else 1)]
     engine.set_option(2, 0)
@@ -264,7 +264,7 @@ def test_match_largest_frames(engine):
     offs = np.r_[0, np.cumsum(counts)]
     outs = {}
     pq, pt = [1, 2, 3], [0, 1, 2]
-    for v in (0, 5, 7):
+    for v in (0, 5, 7, 8, 9):
         engine.set_option(2, v)
         outs[v] = engine.match(st, pq, pt)
     engine.set_option(2, 0)
@@ -277,6 +277,6 @@ def test_match_largest_frames(engine):
         key = d2.double() * 16384 + torch.arange(nt, device="cuda", dtype=torch.float64)[None, :]
         top = torch.topk(key, 2, dim=1, largest=False).values
         idx = (top % 16384).long(); val = torch.div(top, 16384, rounding_mode="floor").long()
-        for v in (0, 5, 7):
+        for v in (0, 5, 7, 8, 9):
             assert torch.equal(outs[v].top2_idx[ro:ro + nq].long(), idx), (v, p)
             assert torch.equal(outs[v].top2_d2[ro:ro + nq].long(), val), (v, p)

@@ -342,7 +342,7 @@ class GeometryEngine:
 
     # ------------------------------------------------------------------ video-level driver
     def _pairs_range(self, st: FrameStore, r: PairResults, p0: int, p1: int, n_hyp, seed, pair_id_base, ratio, thresh,
-                     min_matching_pts=4):
+                     min_matching_pts=4, after_match=None):
         """match_static_kps + compute_homography for pairs [p0, p1) of an already allocated PairResults
         (device pointers offset into the per-pair arrays; per-row arrays are addressed through out_off)."""
         n = p1 - p0
@@ -357,6 +357,8 @@ class GeometryEngine:
                                            _ptr(st.row_off), _ptr(st.n_kp), at(r.pair_q), at(r.pair_t), at(r.out_off), n,
                                            mk, float(ratio), int(min_matching_pts), _ptr(r.surv), _ptr(r.m_idx), _ptr(r.m_pts),
                                            at(r.m_cnt), at(r.n_filtered), at(r.status), strm))
+        if after_match is not None:
+            after_match()
         self._check(lib.evz_find_homography(h, _ptr(r.m_pts), at(r.out_off), at(r.m_cnt), n, mk, None, int(n_hyp),
                                             int(seed) & 0xFFFFFFFF, int(pair_id_base) + p0, 1, float(thresh), 0.0,
                                             _lib.ST_NO_MODEL_1, at(r.status), at(r.H1, 9), _ptr(r.mask1), at(r.inl1),
@@ -367,6 +369,20 @@ class GeometryEngine:
                                             int(seed) & 0xFFFFFFFF, int(pair_id_base) + p0, 2, float(thresh), 0.7,
                                             _lib.ST_NO_MODEL_2, at(r.status), at(r.H, 9), _ptr(r.mask2), at(r.inl2),
                                             at(r.best_hyp2), at(r.best_cnt2), _ptr(r.mask2_best), at(r.extra["H2_best"], 9), strm))
+
+    def alloc_results(self, st: FrameStore, pair_q, pair_t) -> PairResults:
+        """Workspace for `process_pairs_into`: every per-pair / per-row output of the path, allocated once."""
+        pq = torch.as_tensor(pair_q, dtype=torch.int32).to(self.device)
+        pt = torch.as_tensor(pair_t, dtype=torch.int32).to(self.device)
+        return self._alloc_results(st, pq, pt)
+
+    def process_pairs_into(self, st: FrameStore, r: PairResults, n_hyp=1024, seed=0, pair_id_base=0, ratio=0.5, thresh=3.0,
+                           after_match=None) -> PairResults:
+        """`process_pairs` into a workspace from `alloc_results`: no allocation, no memset, nothing but the kernels of the
+        path on the current stream (what a steady-state caller -- and bench.py's timed region -- runs per batch).
+        after_match: optional callable invoked between the match stage and the first RANSAC (event recording)."""
+        self._pairs_range(st, r, 0, int(r.pair_q.numel()), n_hyp, seed, pair_id_base, ratio, thresh, after_match=after_match)
+        return r
 
     def _alloc_results(self, st: FrameStore, pq, pt) -> PairResults:
         P, rows = int(pq.numel()), st.rows

@@ -22,6 +22,7 @@
 // This file is compiled with --fmad=false: the f64 solver must round exactly like the NumPy
 // oracle (oracle/ransac.py) so that identical seeds give bit-identical inlier masks.
 #include "evz_common.cuh"
+#include "evz_ptx.cuh"
 #include <cfloat>
 
 namespace evz {
@@ -139,7 +140,7 @@ struct FhArgs {
 // 8x8 symmetric positive-definite system through an LDL^T factorisation held in registers
 // (all loops unrolled -> static indexing).  A: full symmetric 8x8 (shared memory), diag_add added to
 // the diagonal.  Returns false when a pivot is not positive / finite.
-struct Ldl8 { double L[8][8]; double d[8]; bool ok; };
+struct Ldl8 { double L[8][8]; double d[8]; double inv[8]; bool ok; };
 __device__ __forceinline__ void ldl8_factor(const double* A, const double* diag_add, double lam, Ldl8& f) {
     f.ok = true;
 #pragma unroll
@@ -150,6 +151,7 @@ __device__ __forceinline__ void ldl8_factor(const double* A, const double* diag_
         f.ok = f.ok && (dj > 0.0) && isfinite(dj);
         f.d[j] = dj;
         const double inv = 1.0 / dj;
+        f.inv[j] = inv;
 #pragma unroll
         for (int i = j + 1; i < 8; ++i) {
             double v = A[i * 8 + j];
@@ -170,7 +172,7 @@ __device__ __forceinline__ void ldl8_solve(const Ldl8& f, const double (&b)[8], 
     }
 #pragma unroll
     for (int i = 7; i >= 0; --i) {
-        double v = y[i] / f.d[i];
+        double v = y[i] * f.inv[i];      // the pivot reciprocals of the factorisation: no second set of divisions
 #pragma unroll
         for (int k = i + 1; k < 8; ++k) v -= f.L[k][i] * x[k];
         x[i] = v;
@@ -247,11 +249,27 @@ struct LmShared {
 };
 
 // all threads: accumulate the packed sums at parameters h over the inliers flagged in msk
-__device__ void lm_accumulate(const double* h, const float4* pts, const uint8_t* msk, int m, LmShared& L) {
+// kMakeMask: the first pass also classifies every point with the winner's f32 model (hb, thresh2) and writes the mask
+template <bool kMakeMask>
+__device__ void lm_accumulate(const double* h, const float4* pts, uint8_t* msk, int m, LmShared& L,
+                              const float* hb = nullptr, float thresh2 = 0.f, uint8_t* mask_out = nullptr) {
     double s[kNSums];
 #pragma unroll
     for (int i = 0; i < kNSums; ++i) s[i] = 0.0;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) if (msk[i]) lm_point(h, pts[i], s);
+    if (kMakeMask) {
+        float hf[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hf[i] = hb[i];
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            const float4 pt = pts[i];
+            const uint8_t in = reproj_err32(hf, pt) <= thresh2 ? 1 : 0;
+            msk[i] = in;
+            if (mask_out) mask_out[i] = in;
+            if (in) lm_point(h, pt, s);
+        }
+    } else {
+        for (int i = threadIdx.x; i < m; i += blockDim.x) if (msk[i]) lm_point(h, pts[i], s);
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // warp reduction of the 30 sums as a transposing butterfly: at every step a lane keeps one half of its values
     // and trades the other half, so that lane i ends up with the warp total of sum i (31 exchanges instead of
@@ -655,27 +673,44 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     __shared__ float grp_s[kGrp * 10];
     __shared__ int grp_dead[kGrp];
     __shared__ int s_flag, s_nvalid, s_nsafe, s_nsurv, s_lbest, s_cut, s_leader;
+    __shared__ __align__(8) uint64_t stage_bar;
 
     const int p = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) phase[p] = 0;
-    if (a.status[p] != EVZ_ST_OK) return;
+    // the three per-pair scalars are loaded together (one round trip to L2 instead of three dependent ones)
+    const int st_p = a.status[p];
     const int m = a.cnt[p];
     const int64_t o = a.off[p];
+    if (st_p != EVZ_ST_OK) return;
     if (m < 4) { if (tid == 0) a.status[p] = EVZ_ST_FEW_POINTS; return; }
 
     // stage the point pairs (optionally through matrix_H_prev); track max |coordinate|
     const double* T = a.pre_H ? a.pre_H + static_cast<size_t>(p) * 9 : nullptr;
     float cmax = 0.f;
-    for (int i = tid; i < m; i += blockDim.x) {
-        float4 v = reinterpret_cast<const float4*>(a.pts)[o + i];
-        if (T) {
+    if (T) {
+        for (int i = tid; i < m; i += blockDim.x) {
+            float4 v = reinterpret_cast<const float4*>(a.pts)[o + i];
             const float2 pa = pre_map(T, v.x, v.y), pb = pre_map(T, v.z, v.w);
             v = make_float4(pa.x, pa.y, pb.x, pb.y);
+            pts[i] = v;
+            pos[i] = static_cast<uint16_t>(i);
+            cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
         }
-        pts[i] = v;
-        pos[i] = static_cast<uint16_t>(i);
-        cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    } else {
+        // one bulk copy (TMA) of the pair's contiguous, 16-byte aligned point list
+        if (tid == 0) { mbar_init(&stage_bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&stage_bar, static_cast<uint32_t>(m) * 16u);
+            bulk_load_1d(pts, reinterpret_cast<const float4*>(a.pts) + o, static_cast<uint32_t>(m) * 16u, &stage_bar);
+        }
+        for (int i = tid; i < m; i += blockDim.x) pos[i] = static_cast<uint16_t>(i);
+        mbar_wait(&stage_bar, 0);
+        for (int i = tid; i < m; i += blockDim.x) {
+            const float4 v = pts[i];
+            cmax = fmaxf(cmax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+        }
     }
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffff, cmax, of));
@@ -985,6 +1020,7 @@ ransac_refit_kernel(const FhArgs a, const double* __restrict__ Hbest_in, const i
     uint8_t* msk = fh_smem + static_cast<size_t>(a.max_cnt) * 16;
     __shared__ LmShared L;
     __shared__ int red[kRfThreads / 32];
+    __shared__ __align__(8) uint64_t stage_bar;
 
     const int p = blockIdx.x;
     if (phase[p] != 1) return;
@@ -993,37 +1029,46 @@ ransac_refit_kernel(const FhArgs a, const double* __restrict__ Hbest_in, const i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* T = a.pre_H ? a.pre_H + static_cast<size_t>(p) * 9 : nullptr;
     float cmax = 0.f;
-    for (int i = tid; i < m; i += blockDim.x) {
-        float4 v = reinterpret_cast<const float4*>(a.pts)[o + i];
-        if (T) {
+    if (T) {
+        for (int i = tid; i < m; i += blockDim.x) {
+            float4 v = reinterpret_cast<const float4*>(a.pts)[o + i];
             const float2 pa = pre_map(T, v.x, v.y), pb = pre_map(T, v.z, v.w);
             v = make_float4(pa.x, pa.y, pb.x, pb.y);
+            pts[i] = v;
+            cmax = fmaxf(cmax, fmaxf(fabsf(v.x), fabsf(v.y)));
         }
-        pts[i] = v;
-        cmax = fmaxf(cmax, fmaxf(fabsf(v.x), fabsf(v.y)));
+        if (tid < 8) L.x[tid] = Hbest_in[static_cast<size_t>(p) * 9 + tid];
+    } else {
+        // one bulk copy (TMA, 16 bytes per point) instead of a latency-bound loop of 64-thread loads: the point list of a
+        // pair is contiguous and 16-byte aligned
+        if (tid == 0) { mbar_init(&stage_bar, 1); fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_arrive_expect_tx(&stage_bar, static_cast<uint32_t>(m) * 16u);
+            bulk_load_1d(pts, reinterpret_cast<const float4*>(a.pts) + o, static_cast<uint32_t>(m) * 16u, &stage_bar);
+        }
+        if (tid < 8) L.x[tid] = Hbest_in[static_cast<size_t>(p) * 9 + tid];
+        mbar_wait(&stage_bar, 0);
+        for (int i = tid; i < m; i += blockDim.x) {
+            const float4 v = pts[i];
+            cmax = fmaxf(cmax, fmaxf(fabsf(v.x), fabsf(v.y)));
+        }
     }
 #pragma unroll
     for (int of = 16; of > 0; of >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffff, cmax, of));
     if (lane == 0) L.cmax_w[warp] = cmax;
-    if (tid < 8) L.x[tid] = Hbest_in[static_cast<size_t>(p) * 9 + tid];
     __syncthreads();
 #pragma unroll
     for (int w = 0; w < kRfThreads / 32; ++w) cmax = fmaxf(cmax, L.cmax_w[w]);
     const double cm = static_cast<double>(fmaxf(cmax, 1.f));
 
-    // ---------------- phase 3: winner's inlier mask, then LM refit on it
+    // ---------------- phase 3: winner's inlier mask and the first LM pass over it, in one sweep
     {
         float hb[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) hb[i] = static_cast<float>(L.x[i]);
-        for (int i = tid; i < m; i += blockDim.x) {
-            const uint8_t in = reproj_err32(hb, pts[i]) <= a.thresh2 ? 1 : 0;
-            msk[i] = in;
-            if (a.mask_best) a.mask_best[o + i] = in;
-        }
+        lm_accumulate<true>(L.x, pts, msk, m, L, hb, a.thresh2, a.mask_best ? a.mask_best + o : nullptr);
     }
-    __syncthreads();
-    lm_accumulate(L.x, pts, msk, m, L);
     if (tid == 0) {
         lm_expand(L.sums, L.A, L.v);
         for (int i = 0; i < 8; ++i) L.D[i] = L.A[i * 8 + i];
@@ -1052,7 +1097,7 @@ ransac_refit_kernel(const FhArgs a, const double* __restrict__ Hbest_in, const i
                               fmax(fabs(d[6]), fabs(d[7])) * cm * cm;
             if (f.ok && px < kPxTol) break;
         }
-        lm_accumulate(xd, pts, msk, m, L);
+        lm_accumulate<false>(xd, pts, msk, m, L);
         if (tid == 0) {
             const double Sd = L.sums[29];
             double dS = 0.0, tdv = 0.0, dmax = 0.0;

@@ -135,6 +135,7 @@ struct FhArgs {
     int max_cnt;
     int exact_only;
     int no_prune;
+    float4* hcache;     // [n_pairs][n_hyp][2] f32 models of the hypotheses that passed pass 0 (null: solved again where needed)
 };
 
 // 8x8 symmetric positive-definite system through an LDL^T factorisation held in registers
@@ -376,6 +377,28 @@ __device__ __forceinline__ void load_sample(const float4* pts, const uint16_t* p
     for (int k = 0; k < 4; ++k) q[k] = pts[pos[idx[k]]];
 }
 
+// f32 model of hypothesis `hyp`: pass 0 solved it once (f64, cast to f32) and left it in the per-pair model cache in
+// global memory (32 bytes, an L2 hit a few microseconds later); without a cache the sample is drawn and solved again.
+// A staged level-1 scoring looks at a surviving hypothesis once per stage and a sliced row once per slice: the
+// closed-form solve (~150 f64 instructions) is several times the price of the two loads.
+__device__ __forceinline__ void hyp_model(const FhArgs& a, const float4* pts, const uint16_t* pos, int hyp, int m,
+                                          uint32_t pair_level, float (&hf)[8]) {
+    if (a.hcache) {
+        const float4* hc = a.hcache + (static_cast<size_t>(blockIdx.x) * a.n_hyp + hyp) * 2;
+        const float4 u = __ldcg(hc), v = __ldcg(hc + 1);
+        hf[0] = u.x; hf[1] = u.y; hf[2] = u.z; hf[3] = u.w; hf[4] = v.x; hf[5] = v.y; hf[6] = v.z; hf[7] = v.w;
+    } else {
+        int idx[4];
+        sample4(a.seed, pair_level, static_cast<uint32_t>(hyp), m, idx);
+        float4 q[4];
+        load_sample(pts, pos, idx, q);
+        double H[9];
+        solve4(q, H);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) hf[i] = static_cast<float>(H[i]);
+    }
+}
+
 template <int NJ, bool kCheckDen>
 __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, const uint16_t* pos, const uint16_t* vlist,
                                            uint16_t* lo_s, uint16_t* hi_s, int s0, int n_valid, int m, float cmax,
@@ -395,14 +418,7 @@ __device__ __forceinline__ int score_batch(const FhArgs& a, const float4* pts, c
         for (int i = 0; i < 8; ++i) hf[j][i] = 0.f;
         // hypotheses behind the cut (see the pruning note in ransac_score_kernel) stay idle: lo = hi = 0
         if (slot < n_valid && static_cast<int>(vlist[slot]) < cutv) {
-            int idx[4];
-            sample4(a.seed, pair_level, static_cast<uint32_t>(vlist[slot]), m, idx);
-            float4 q[4];
-            load_sample(pts, pos, idx, q);
-            double H[9];
-            solve4(q, H);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) hf[j][i] = static_cast<float>(H[i]);
+            hyp_model(a, pts, pos, vlist[slot], m, pair_level, hf[j]);
             fused_thresholds(hf[j], cmax, a.thresh2, a.exact_only != 0, tlo[j], thi[j]);
             any_live = true;
             if (rg.mode == kSuffix || rg.mode == kMid) { lo[j] = lo_s[slot]; out[j] = hi_s[slot]; }
@@ -464,14 +480,7 @@ __device__ __forceinline__ void score_partial_row(const FhArgs& a, const float4*
 #pragma unroll
     for (int i = 0; i < 8; ++i) hf[i] = 0.f;
     if (live) {
-        int idx[4];
-        sample4(a.seed, pair_level, static_cast<uint32_t>(vlist[r0 + k]), m, idx);
-        float4 q[4];
-        load_sample(pts, pos, idx, q);
-        double H[9];
-        solve4(q, H);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) hf[i] = static_cast<float>(H[i]);
+        hyp_model(a, pts, pos, vlist[r0 + k], m, pair_level, hf);
         fused_thresholds(hf, cmax, a.thresh2, a.exact_only != 0, tlo, thi);
     }
     part[tid] = 0; part[kRsThreads + tid] = 0;
@@ -762,6 +771,11 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
                 double H[9];
                 ok = solve4(q, H) ? 1 : 0;
                 safe = ok && den_safe(static_cast<float>(H[6]), static_cast<float>(H[7]), cmax);
+                if (ok && a.hcache) {
+                    float4* hc = a.hcache + (static_cast<size_t>(p) * a.n_hyp + hyp) * 2;
+                    __stcg(hc, make_float4(static_cast<float>(H[0]), static_cast<float>(H[1]), static_cast<float>(H[2]), static_cast<float>(H[3])));
+                    __stcg(hc + 1, make_float4(static_cast<float>(H[4]), static_cast<float>(H[5]), static_cast<float>(H[6]), static_cast<float>(H[7])));
+                }
             }
             const unsigned bal_s = __ballot_sync(0xffffffff, safe);
             const unsigned bal_u = __ballot_sync(0xffffffff, ok && !safe);
@@ -1200,10 +1214,15 @@ extern "C" int evz_find_homography(evz_handle* h, const float* pts, const int32_
     // scratch: phase[P] | H_best[P][9] when the caller does not want it
     void* scr = nullptr;
     const size_t ph_bytes = evz_align_up(static_cast<size_t>(n_pairs) * 4, 256);
-    int rc = evz_scratch(h, ph_bytes + (H_best ? 0 : static_cast<size_t>(n_pairs) * 72) + 256, &scr);
+    const size_t hb_bytes = evz_align_up(H_best ? 0 : static_cast<size_t>(n_pairs) * 72, 256);
+    // model cache of the scoring kernel (hyp_model): 32 bytes per hypothesis, written and read by the pair's own CTA
+    size_t hc_bytes = static_cast<size_t>(n_pairs) * static_cast<size_t>(n_hyp) * 32;
+    if (hc_bytes > (size_t(4) << 30) || h->opt_ransac_exact) hc_bytes = 0;
+    int rc = evz_scratch(h, ph_bytes + hb_bytes + hc_bytes + 256, &scr);
     if (rc) return rc;
     int32_t* phase = static_cast<int32_t*>(scr);
     double* hb = H_best ? H_best : reinterpret_cast<double*>(static_cast<uint8_t*>(scr) + ph_bytes);
+    float4* hcache = hc_bytes ? reinterpret_cast<float4*>(static_cast<uint8_t*>(scr) + ph_bytes + hb_bytes) : nullptr;
     EVZ_REQUIRE(h, n_hyp <= 65535, "n_hyp must be below 65536");
     const int smem_score = max_cnt * 16 + ((max_cnt + 7) & ~7) * 2 + 8 * n_hyp + 16;
     const int smem_refit = max_cnt * 17 + 16;
@@ -1217,7 +1236,7 @@ extern "C" int evz_find_homography(evz_handle* h, const float* pts, const int32_
     }
     const float t = static_cast<float>(thresh * thresh);
     evz::FhArgs a{pts, off, cnt, pre_H, n_hyp, seed, pair_id_base, level, t, min_inlier_frac, fail_status,
-                  status, H, mask, inl_cnt, best_hyp, best_cnt, mask_best, H_best, max_cnt, h->opt_ransac_exact, h->opt_ransac_no_prune};
+                  status, H, mask, inl_cnt, best_hyp, best_cnt, mask_best, H_best, max_cnt, h->opt_ransac_exact, h->opt_ransac_no_prune, hcache};
     evz::ransac_score_kernel<<<n_pairs, evz::kRsThreads, smem_score, st>>>(a, hb, phase);
     EVZ_LAUNCH_CHECK(h);
     evz::ransac_refit_kernel<<<n_pairs, evz::kRfThreads, smem_refit, st>>>(a, hb, phase);

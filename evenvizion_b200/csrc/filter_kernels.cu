@@ -145,10 +145,12 @@ struct FilterArgs {
     uint8_t* surv; int32_t* m_idx; float* m_pts; int32_t* m_cnt; int32_t* n_filtered; int32_t* status;
 };
 
-// one CTA per pair
+// one CTA per pair.  Every thread owns FOUR consecutive queries of a sweep (128-bit loads of the top-2 records, the
+// canonical indices and the coordinates; one block scan per 2048 queries): the kernel is a chain of dependent
+// round trips to L2, so the fewer sweeps and the more loads in flight per trip the better.
 __global__ void __launch_bounds__(512)
 filter_matches_kernel(const FilterArgs a) {
-    extern __shared__ int32_t fsm[];
+    extern __shared__ __align__(16) int32_t fsm[];
     __shared__ int warp_sums[32];
     __shared__ int kept_total;
     const int p = blockIdx.x;
@@ -156,40 +158,63 @@ filter_matches_kernel(const FilterArgs a) {
     const int nq = a.n_kp[qf], nt = a.n_kp[tf];
     const int q0 = a.row_off[qf], t0 = a.row_off[tf];
     const int64_t o0 = a.out_off[p];
-    int32_t* tsel = fsm;              // [nq] claimed train index of a surviving query, else -1
-    int32_t* first_c = tsel + nq;     // [nq] smallest kept query of a coordinate group
-    int32_t* last_c = first_c + nq;   // [nq] largest kept query of a coordinate group
-    int32_t* cnt_t = last_c + nq;     // [nt] surviving queries per train index
+    const int nq4 = (nq + 3) & ~3;    // the arrays below are padded to a multiple of 4 (the per-row arrays of a frame to 256)
+    int32_t* tsel = fsm;              // [nq4] claimed train index of a surviving query, else -1
+    int32_t* first_c = tsel + nq4;    // [nq4] smallest kept query of a coordinate group
+    int32_t* last_c = first_c + nq4;  // [nq4] largest kept query of a coordinate group
+    int32_t* cnt_t = last_c + nq4;    // [nt] surviving queries per train index
     for (int i = threadIdx.x; i < nq; i += blockDim.x) { first_c[i] = INT_MAX; last_c[i] = -1; }
     for (int i = threadIdx.x; i < nt; i += blockDim.x) cnt_t[i] = 0;
     if (threadIdx.x == 0) kept_total = 0;
     __syncthreads();
+    const int sweep = blockDim.x * 4;
     // Lowe ratio test: matches[0].distance < matches[1].distance * ratio, f32 sqrt, double compare
-    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
-        const int2 id = reinterpret_cast<const int2*>(a.top2_idx)[o0 + q];
-        const int2 dd = reinterpret_cast<const int2*>(a.top2_d2)[o0 + q];
-        bool s = false;
-        if (id.y >= 0) {
-            const double d0 = static_cast<double>(__fsqrt_rn(static_cast<float>(dd.x)));
-            const double d1 = static_cast<double>(__fsqrt_rn(static_cast<float>(dd.y)));
-            s = d0 < __dmul_rn(d1, a.ratio);
+    for (int qb = 0; qb < nq; qb += sweep) {
+        const int q = qb + 4 * threadIdx.x;
+        if (q >= nq) continue;
+        // (64-bit loads: out_off[p] is only known to be a row number, and a pair owns exactly n_kp rows)
+        const int2* pi = reinterpret_cast<const int2*>(a.top2_idx) + o0 + q;
+        const int2* pd = reinterpret_cast<const int2*>(a.top2_d2) + o0 + q;
+        const int2 none = make_int2(-1, -1);
+        const int2 i0 = pi[0], i1 = q + 1 < nq ? pi[1] : none, i2 = q + 2 < nq ? pi[2] : none, i3 = q + 3 < nq ? pi[3] : none;
+        const int2 d0v = pd[0], d1v = q + 1 < nq ? pd[1] : none, d2v = q + 2 < nq ? pd[2] : none, d3v = q + 3 < nq ? pd[3] : none;
+        const int id0[4] = {i0.x, i1.x, i2.x, i3.x}, id1[4] = {i0.y, i1.y, i2.y, i3.y};
+        const int dd0[4] = {d0v.x, d1v.x, d2v.x, d3v.x}, dd1[4] = {d0v.y, d1v.y, d2v.y, d3v.y};
+        int sel[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bool s = false;
+            if (q + k < nq && id1[k] >= 0) {
+                const double d0 = static_cast<double>(__fsqrt_rn(static_cast<float>(dd0[k])));
+                const double d1 = static_cast<double>(__fsqrt_rn(static_cast<float>(dd1[k])));
+                s = d0 < __dmul_rn(d1, a.ratio);
+            }
+            sel[k] = s ? id0[k] : -1;
+            if (a.surv && q + k < nq) a.surv[o0 + q + k] = s ? 1 : 0;
+            if (s) atomicAdd(&cnt_t[id0[k]], 1);
         }
-        tsel[q] = s ? id.x : -1;
-        if (a.surv) a.surv[o0 + q] = s ? 1 : 0;
-        if (s) atomicAdd(&cnt_t[id.x], 1);
+        *reinterpret_cast<int4*>(tsel + q) = make_int4(sel[0], sel[1], sel[2], sel[3]);
     }
     __syncthreads();
     // many-to-one filter, then group the kept queries by coordinate
     int kept = 0;
-    for (int q = threadIdx.x; q < nq; q += blockDim.x) {
-        int t = tsel[q];
-        if (t >= 0 && cnt_t[t] != 1) { t = -1; tsel[q] = -1; }
-        if (t >= 0) {
-            ++kept;
-            const int c = a.canon[q0 + q];
-            atomicMin(&first_c[c], q);
-            atomicMax(&last_c[c], q);
+    for (int qb = 0; qb < nq; qb += sweep) {
+        const int q = qb + 4 * threadIdx.x;
+        if (q >= nq) continue;
+        const int4 cn = *reinterpret_cast<const int4*>(a.canon + q0 + q);
+        int4 ts = *reinterpret_cast<const int4*>(tsel + q);
+        int sel[4] = {ts.x, ts.y, ts.z, ts.w};
+        const int cc[4] = {cn.x, cn.y, cn.z, cn.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (sel[k] >= 0 && cnt_t[sel[k]] != 1) sel[k] = -1;
+            if (sel[k] >= 0) {
+                ++kept;
+                atomicMin(&first_c[cc[k]], q + k);
+                atomicMax(&last_c[cc[k]], q + k);
+            }
         }
+        *reinterpret_cast<int4*>(tsel + q) = make_int4(sel[0], sel[1], sel[2], sel[3]);
     }
     if (kept) atomicAdd(&kept_total, kept);
     __syncthreads();
@@ -199,17 +224,35 @@ filter_matches_kernel(const FilterArgs a) {
     int base = 0;
     const float2* cq = reinterpret_cast<const float2*>(a.coords) + q0;
     const float2* ct = reinterpret_cast<const float2*>(a.coords) + t0;
-    for (int qb = 0; qb < nq; qb += blockDim.x) {
-        const int q = qb + threadIdx.x;
-        int emit = 0, c = 0;
-        if (ok && q < nq && tsel[q] >= 0) { c = a.canon[q0 + q]; emit = first_c[c] == q; }
+    for (int qb = 0; qb < nq; qb += sweep) {
+        const int q = qb + 4 * threadIdx.x;
+        int emit[4] = {0, 0, 0, 0}, tr[4] = {0, 0, 0, 0};
+        float2 pa[4], pb[4];
+        int n_emit = 0;
+        if (ok && q < nq) {
+            const int4 ts = *reinterpret_cast<const int4*>(tsel + q);
+            const int4 cn = *reinterpret_cast<const int4*>(a.canon + q0 + q);
+            const int sel[4] = {ts.x, ts.y, ts.z, ts.w}, cc[4] = {cn.x, cn.y, cn.z, cn.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (q + k < nq && sel[k] >= 0 && first_c[cc[k]] == q + k) {
+                    emit[k] = 1;
+                    tr[k] = tsel[last_c[cc[k]]];
+                    pa[k] = cq[q + k];             // the gathers leave before the scan and land behind it
+                    pb[k] = ct[tr[k]];
+                    ++n_emit;
+                }
+            }
+        }
         int total;
-        const int pos = base + block_excl_scan(emit, warp_sums, total);
-        if (emit) {
-            const int t = tsel[last_c[c]];
-            const float2 pa = cq[q], pb = ct[t];
-            reinterpret_cast<int2*>(a.m_idx)[o0 + pos] = make_int2(q, t);
-            reinterpret_cast<float4*>(a.m_pts)[o0 + pos] = make_float4(pa.x, pa.y, pb.x, pb.y);
+        int pos = base + block_excl_scan(n_emit, warp_sums, total);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (emit[k]) {
+                reinterpret_cast<int2*>(a.m_idx)[o0 + pos] = make_int2(q + k, tr[k]);
+                reinterpret_cast<float4*>(a.m_pts)[o0 + pos] = make_float4(pa[k].x, pa[k].y, pb[k].x, pb[k].y);
+                ++pos;
+            }
         }
         base += total;
         __syncthreads();
@@ -342,7 +385,7 @@ extern "C" int evz_filter_matches(evz_handle* h, const int32_t* top2_idx, const 
     }
     if (n_pairs <= 0) return EVZ_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int smem = 16 * (max_kp > 0 ? max_kp : 1);
+    const int smem = 16 * (max_kp > 0 ? max_kp : 1) + 64;      // three tables padded to a multiple of 4 entries
     if (smem > h->attr_filter) {
         EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::filter_matches_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         h->attr_filter = smem;

@@ -34,6 +34,7 @@ constexpr int kGrp = 32;          // hypotheses per group of the level-2 search 
 constexpr int kStagesMax = 6;     // stages of the level-1 staged scoring
 constexpr int kLmMaxIters = 20;   // OpenCV uses 10 from a DLT start; we start from the 4-point model
 constexpr double kPxTol = 1e-6;   // LM stops when a step moves every point by less than this many pixels
+constexpr double kPxApply = 1e-3; // an undamped step smaller than this is applied without a confirming pass (see the LM loop)
 constexpr int kNSums = 32;        // 21 JtJ + 8 Jtr + S + max|r| (+1 pad)
 
 __device__ __forceinline__ uint32_t mix32(uint32_t x) {
@@ -1110,6 +1111,15 @@ ransac_refit_kernel(const FhArgs a, const double* __restrict__ Hbest_in, const i
             const double px = fmax(fmax(fabs(d[0]), fabs(d[1])), fmax(fabs(d[3]), fabs(d[4]))) * cm + fmax(fabs(d[2]), fabs(d[5])) +
                               fmax(fabs(d[6]), fabs(d[7])) * cm * cm;
             if (f.ok && px < kPxTol) break;
+            // an undamped step below kPxApply pixels is taken without the pass that would only confirm it: the step
+            // after it is smaller by the contraction factor of Gauss-Newton near the optimum (~1e-3 on these problems),
+            // i.e. far below kPxTol, so x - d is the point the full iteration stops at as well
+            if (f.ok && px < kPxApply && L.lam == 0.0) {
+                __syncthreads();
+                if (tid < 8) L.x[tid] = xd[tid];
+                __syncthreads();
+                break;
+            }
         }
         lm_accumulate<false>(xd, pts, msk, m, L);
         if (tid == 0) {

@@ -47,16 +47,16 @@ KERNELS_PER_STEP_MULTI = 6 + 1 + 2 + 1 + 2 + 10
 # dram__bytes_read.sum + dram__bytes_write.sum of one match_top2_vkernel<0> launch (the kernel as it ships) at config 2 x
 # 10 000 pairs: ncu --set full capture of round 2, profiles/r02_prof_vkernel_raw.csv
 MATCH_TRAFFIC_BYTES = {(2, 10000): 3449581000 + 324503808}
-# ncu --set full of the RANSAC kernels as they ship (profiles/r02_prof_{score,refit}_raw.csv; 2000 pairs of config 2:
+# ncu --set full of the RANSAC kernels as they ship (profiles/r02b_prof_{score,refit}_raw.csv; 2000 pairs of config 2:
 # 1229 matches at level 1, 584 static points at level 2, 1024 hypotheses)
 RANSAC_NCU = {
-    "source": "profiles/r02_prof_score_raw.csv, profiles/r02_prof_refit_raw.csv (2000 pairs of config 2)",
-    "score_level1": {"us": 592.2, "issue_slots_pct": 75.0, "sm_throughput_pct": 69.4, "fma_pipe_pct": 34.1, "alu_pipe_pct": 45.2,
-                     "dram_pct": 0.8, "warp_instr_per_nominal_eval": 465.4e6 / (2000 * 1024 * 1229.0)},
-    "score_level2": {"us": 104.9, "issue_slots_pct": 60.1, "sm_throughput_pct": 45.1, "dram_pct": 2.2,
-                     "warp_instr_per_nominal_eval": 52.7e6 / (2000 * 1024 * 584.0)},
-    "refit_level1": {"us": 149.7, "issue_slots_pct": 37.5, "fp64_pipe_pct": 33.8, "dram_pct": 3.2},
-    "refit_level2": {"us": 106.0, "issue_slots_pct": 39.0, "fp64_pipe_pct": 34.6, "dram_pct": 2.2},
+    "source": "profiles/r02b_prof_score_raw.csv, profiles/r02b_prof_refit_raw.csv (2000 pairs of config 2)",
+    "score_level1": {"us": 564.7, "issue_slots_pct": 73.3, "sm_throughput_pct": 68.4, "fma_pipe_pct": 35.2, "alu_pipe_pct": 44.4,
+                     "dram_pct": 1.5, "warp_instr_per_nominal_eval": 434.9e6 / (2000 * 1024 * 1229.0)},
+    "score_level2": {"us": 101.9, "issue_slots_pct": 61.1, "sm_throughput_pct": 44.9, "dram_pct": 2.3,
+                     "warp_instr_per_nominal_eval": 53.0e6 / (2000 * 1024 * 584.0)},
+    "refit_level1": {"us": 101.5, "issue_slots_pct": 43.6, "fp64_pipe_pct": 41.0, "dram_pct": 4.8},
+    "refit_level2": {"us": 67.6, "issue_slots_pct": 44.5, "fp64_pipe_pct": 41.4, "dram_pct": 3.4},
 }
 
 def peaks():

@@ -1,5 +1,6 @@
 """The reference-facing Python API (evenvizion_b200.processing) on the GPU.  Needs a B200."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -280,6 +281,42 @@ def test_get_homography_dict_on_capture(proc, clip):
         assert np.abs(a[:, :2] / a[:, 2:] - b[:, :2] / b[:, 2:]).max() < 1e-2, k
     with pytest.raises(ValueError):
         proc.get_homography_dict(_FakeCapture([]))             # unreadable first frame (video_processing.py:60-61)
+
+
+def test_example_cli_outputs(proc, clip, bundled, tmp_path):
+    """examples/evenvizion_component.py (the reference's component.py:102-146 without the drawing layer): the three files it
+    writes are what the package API gives for the same capture -- dict_with_homography_matrix.json re-readable by
+    read_homography_dict, metrics_file.txt = evz_max_movement over frames 1 .. F-1, the fixed-coordinate JSON =
+    from_original_to_fix on the frames the capture holds."""
+    pytest.importorskip("cv2")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("evz_example_component", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "evenvizion_component.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    frames = [clip[f"frame{f}"] for f in range(5)]
+    oc = {k: v for k, v in bundled["original_coordinates"].items() if int(k) <= 5}
+    src = tmp_path / "original_coordinates.json"
+    src.write_text(json.dumps(oc))
+    out = mod.run(_FakeCapture(frames), bundled["original_shape"], str(tmp_path / "exp" / "clip"), str(src), True, True, True,
+                  n_hyp=1024, seed=0)
+    assert sorted(out) == ["fixed", "homography", "metrics"]
+    hd = proc.get_homography_dict(_FakeCapture(frames), none_H_processing=True, n_hyp=1024, seed=0)
+    with open(out["homography"]) as f:
+        on_disk = json.load(f)
+    assert list(on_disk) == ["2", "3", "4", "5", "resize_info"]                       # string keys, ascending (component.py:139-140)
+    assert on_disk == json.loads(json.dumps(hd))
+    hm, ri = proc.read_homography_dict(out["homography"])
+    sup = proc.superposition_dict(hm)
+    with open(out["fixed"]) as f:
+        fixed = json.load(f)
+    want = proc.from_original_to_fix(proc.read_json_with_coordinates(str(src)), sup, bundled["original_shape"], [ri["h"], ri["w"]])
+    assert fixed == json.loads(json.dumps(want)) and sorted(fixed, key=int) == ["1", "2", "3", "4", "5"]
+    txt = open(out["metrics"]).read()
+    assert txt.startswith("Maximum movement during the entire video: ")
+    mm = float(txt.split(": ")[1])
+    # the dense metric against the oracle's restatement of heatmap_video_processing (processing_visualization.py:404-418)
+    best = chain.max_movement(sup, ri["h"], ri["w"])
+    assert abs(mm - best) < 1e-9 * max(1.0, abs(best))
 
 
 def test_video_geometry_streamed_equals_single_batch(engine):

@@ -803,6 +803,28 @@ __device__ __forceinline__ void drain_v(uint32_t taddr, uint32_t mul, uint32_t& 
     }
 }
 
+// timing probe (kDbg = 3): one column half (128 columns, chunk tags b0 * 2 ...) of an accumulator row
+__device__ __forceinline__ void drain_v_half(uint32_t taddr, int b0, uint32_t mul, uint32_t& M1, uint32_t& M2, uint32_t& M3,
+                                             uint32_t& sec, uint32_t sum, uint64_t* acc_empty, int lane) {
+    uint32_t r[2][32];
+    tmem_ld_32x32b_x32(taddr, r[0]);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        tmem_ld_wait_dep(r[b & 1]);
+        if (b + 1 < 4) {
+            tmem_ld_32x32b_x32(taddr + (b + 1) * 32, r[(b + 1) & 1]);
+        } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+#pragma unroll
+        for (int c = 0; c < 32 / kVC; ++c) vchunk(&r[b & 1][kVC * c], 254 - (32 / kVC) * (b0 + b) - c, mul, M1, M2, M3, sec, sum);
+        keep_alive16(&r[b & 1][0]);
+        keep_alive16(&r[b & 1][16]);
+    }
+}
+
 // kDbg (EVZ_OPT_MATCH_DEBUG, measurement only): 1 = accumulators released undrained, 2 = TMEM loads only; the
 // production instance is kDbg = 0 (a run-time test in the tile loop costs 1.4 %).
 template <int kDbg>
@@ -833,7 +855,7 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
         for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1 + 8);
-            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kDbg == 3 ? 8 : 4);
         }
         fence_mbar_init();
     }
@@ -933,6 +955,71 @@ match_top2_vkernel(const __grid_constant__ CUtensorMap tmap, const MatchArgs arg
                 }
                 umma_commit(&q_empty[qb]);
             }
+        }
+    } else if (kDbg == 3 && warp >= 4) {
+        // ------------------------------------------------------------- timing probe: all eight drain warps work on ONE
+        // accumulator at a time (column halves), then on the other.  The two halves of a row share their save slots, so
+        // the RESULTS ARE WRONG; the instruction and shared-memory traffic are those of a kernel with per-half slots.
+        const int half = (warp - 4) >> 2;
+        const int quarter = warp & 3;
+        uint32_t g = 0, qi = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const uint32_t qb = qi & 1, qph = (qi >> 1) & 1;
+            ++qi;
+            mbar_wait(&q_full[qb], qph);
+            const Item im = item_s[qb];
+            uint32_t M1[2] = {0, 0}, M2[2] = {0, 0}, M3[2] = {0, 0}, sec[2], sum[2];
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+                const int row = sub * 128 + quarter * 32 + lane;
+                const uint32_t slot_a = smem_u32(smem + Cfg::slot_off) + row * 16, slot_b = slot_a + Cfg::slot_stride;
+                sum[sub] = slot_a + slot_b; sec[sub] = slot_b;
+            }
+            for (int n = 0; n < im.n_tiles; ++n) {
+#pragma unroll
+                for (int sub = 0; sub < 2; ++sub) {
+                    if (sub < im.n_sub) {
+                        M1[sub] |= 255u; M2[sub] |= 255u; M3[sub] |= 255u;
+                        mbar_wait(&acc_full[sub], g & 1);
+                        tc_fence_after();
+                        const uint32_t taddr = tmem_base + sub * kBlockT + half * 128 + (static_cast<uint32_t>(quarter * 32) << 16);
+                        drain_v_half(taddr, half * 4, args.mul256, M1[sub], M2[sub], M3[sub], sec[sub], sum[sub], &acc_empty[sub], lane);
+                    }
+                }
+                ++g;
+            }
+            // end of item: the cost of the exact evaluation of two slots per tracker (values discarded)
+            int acc = 0;
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+                if (sub < im.n_sub) {
+                    int k[2 * kVC];
+#pragma unroll
+                    for (int sidx = 0; sidx < 2; ++sidx) {
+                        const uint32_t sa = sidx == 0 ? sum[sub] - sec[sub] : sec[sub];
+#pragma unroll
+                        for (int part = 0; part < kVC / 4; ++part) {
+                            const int4 v = lds128(sa + part * Cfg::part_stride);
+                            k[sidx * kVC + part * 4 + 0] = mad_key(v.x, args.neg512, part);
+                            k[sidx * kVC + part * 4 + 1] = mad_key(v.y, args.neg512, part + 1);
+                            k[sidx * kVC + part * 4 + 2] = mad_key(v.z, args.neg512, part + 2);
+                            k[sidx * kVC + part * 4 + 3] = mad_key(v.w, args.neg512, part + 3);
+                        }
+                    }
+                    int m1 = INT_MAX, m2 = INT_MAX;
+#pragma unroll
+                    for (int i = 0; i < kVC; ++i) top2_pair(k[2 * i], k[2 * i + 1], m1, m2);
+                    acc += m1 ^ m2 ^ static_cast<int>(M3[sub]);
+                }
+            }
+            const int row0 = quarter * 32 + lane;
+            if (half == 0 && row0 < im.nq_left) {
+                const int64_t o_row = static_cast<int64_t>(im.out_row0) + row0;
+                reinterpret_cast<int2*>(args.top2_idx)[o_row] = make_int2(acc, -1);
+                reinterpret_cast<int2*>(args.top2_d2)[o_row] = make_int2(acc, -1);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&q_empty[qb]);
         }
     } else if (warp >= 4) {
         // ------------------------------------------------------------- epilogue
@@ -2228,6 +2315,7 @@ extern "C" int evz_match_top2_d(evz_handle* h, const uint8_t* desc, int desc_byt
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
+            EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_vkernel_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfgT<2>::smem_bytes));
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_wkernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::VCfg::smem_bytes));
             EVZ_CUDA_CHECK(h, cudaFuncSetAttribute(evz::match_top2_xkernel, cudaFuncAttributeMaxDynamicSharedMemorySize, evz::XCfg::smem_bytes));
@@ -2263,6 +2351,8 @@ extern "C" int evz_match_top2_d(evz_handle* h, const uint8_t* desc, int desc_byt
             evz::match_top2_vkernel<1><<<h->sm_count, evz::VCfg::threads, evz::VCfg::smem_bytes, st>>>(h->tmap, a);
         } else if (h->opt_match_debug == 2) {
             evz::match_top2_vkernel<2><<<h->sm_count, evz::VCfg::threads, evz::VCfg::smem_bytes, st>>>(h->tmap, a);
+        } else if (h->opt_match_debug == 3) {
+            evz::match_top2_vkernel<3><<<h->sm_count, evz::VCfg::threads, evz::VCfg::smem_bytes, st>>>(h->tmap, a);
         } else {
             evz::match_top2_vkernel<0><<<h->sm_count, evz::VCfg::threads, evz::VCfg::smem_bytes, st>>>(h->tmap, a);
         }

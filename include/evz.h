@@ -103,7 +103,8 @@ int         evz_sm_count(const evz_handle* h);
                                      16 pairs, one per call); read them with evz_match_kernel_ms after synchronising */
 #define EVZ_OPT_MATCH_DEBUG    5  /* measurement only, NOT result-preserving (outputs are undefined): 1 = the V-space epilogue releases
                                      every accumulator without draining it (times the TMA / tcgen05 front end alone); 2 = it loads
-                                     every accumulator column from TMEM but does no arithmetic and no saves */
+                                     every accumulator column from TMEM but does no arithmetic and no saves; 3 = all eight drain warps work on
+                                     one accumulator at a time (column halves sharing their save slots): the timing of an eight-warp drain */
 int         evz_set_option(evz_handle* h, int option, int value);
 /* elapsed time of the main match kernel of the k-th most recent evz_match_top2 call (k = 0: the last one), for the
  * roofline line of bench.py.  The stream must have been synchronised; returns EVZ_E_ARG when no such record exists. */

@@ -59,6 +59,16 @@ RANSAC_NCU = {
     "refit_level2": {"us": 67.6, "issue_slots_pct": 44.5, "fp64_pipe_pct": 41.4, "dram_pct": 3.4},
 }
 
+def config_dict(cfg, args, world):
+    """The `config` object of the JSON line: the same for both arms (--impl ours / reference), so that the driver can tell
+    that they ran the same workload; what a run measured about its data goes to `run_stats`."""
+    P = args.pairs if args.pairs else cfg["pairs"]
+    if cfg.get("strong"):
+        P = P // world
+    return {"workload": cfg["name"], "n_kp": cfg["n_kp"], "pairs_per_gpu": P, "n_hyp": cfg["n_hyp"], "parallelism": f"pair-range x{world}",
+            "l2": f"inputs {(P + 1) * cfg['n_kp'] * 136 / 1e9:.1f} GB per step > 126 MB L2, no flush"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -168,7 +178,7 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": "frame-pairs/sec (match+RANSAC H)", "value": v, "unit": "pairs/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (OpenCV CPU)", "data": "synthetic",
-        "config": {"workload": cfg["name"], "n_kp": cfg["n_kp"], "sample_pairs": n},
+        "config": config_dict(cfg, args, args.gpus), "run_stats": {"sample_pairs": n, "pairs_with_valid_H": ok},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -488,9 +498,8 @@ def run_ours(args, cfg):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "u8 (s32 accumulate) match; f32/f64 RANSAC", "data": "synthetic",
-            "config": {"workload": cfg["name"], "n_kp": N, "pairs_per_gpu": P, "n_hyp": n_hyp, "parallelism": f"pair-range x{world}",
-                       "l2": f"inputs {(P + 1) * N * 136 / 1e9:.1f} GB per step > 126 MB L2, no flush", "valid_pairs_last_step": n_ok,
-                       "mean_matches_per_pair": mean_matches, "mean_static_points_per_pair": mean_static},
+            "config": config_dict(cfg, args, world),
+            "run_stats": {"valid_pairs_last_step": n_ok, "mean_matches_per_pair": mean_matches, "mean_static_points_per_pair": mean_static},
             "stage_ms": {"match": m_ms, "ransac_static_ransac": r_ms, "scan": s_ms, "remap": rm_ms},
             "parity_check": parity,
             "roofline": {"kernel": "match_top2_vkernel", "bound": "tensor", "unit": "TFLOP/s",

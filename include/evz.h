@@ -182,7 +182,8 @@ int evz_filter_matches(evz_handle* h, const int32_t* top2_idx, const int32_t* to
  *   H          DEV double [P][9]  refined homography, h22 = 1: Levenberg-Marquardt on the 8 free parameters over the
  *                                 winner's inlier set (OpenCV's damping schedule and stop rule), started from the winning
  *                                 4-point model -- not from a normalised DLT as cv2 does; same optimum (<= 1e-3 px),
- *                                 first step undamped, stop when a step moves no point by more than 1e-6 px, <= 20 steps
+ *                                 first step undamped, stop when a step moves no point by more than 1e-6 px (an undamped
+ *                                 step below 1e-3 px is applied without a confirming pass), <= 20 steps
  *   mask       DEV uint8 [rows]   final inlier mask: f32 reprojection error of the REFINED H <= thresh^2.  This is what
  *                                 cv2 >= 4.x returns (the oracle is pinned to cv2 4.13); the opencv-contrib 3.4.2 pinned by
  *                                 the reference's requirements.txt returns the RANSAC consensus mask (= mask_best) instead,
@@ -192,6 +193,8 @@ int evz_filter_matches(evz_handle* h, const int32_t* top2_idx, const int32_t* to
  *   best_cnt   DEV int32 [P]      its inlier count
  *   mask_best  DEV uint8 [rows]   its inlier mask (the refit set)
  *   H_best     DEV double [P][9]  its 4-point model
+ * Handle scratch used by this call: 4 B + 72 B per pair, plus a model cache of 32 B per (pair, hypothesis) when that stays
+ * below 4 GB (without it every scoring stage solves its hypotheses again; the results are the same).
  */
 int evz_find_homography(evz_handle* h, const float* pts, const int32_t* off, const int32_t* cnt, int n_pairs,
                         int max_cnt, const double* pre_H, int n_hyp, uint32_t seed, int64_t pair_id_base, int level,

@@ -84,6 +84,54 @@ def test_match_ragged_pairs(engine):
         _check_pair(engine, st, r, p, frames, qf, tf)
 
 
+def test_match_compact_output_rows_through_the_c_abi(engine):
+    """include/evz.h: out_off[p] is any row of the per-row output arrays with room for n_kp[pair_q[p]] rows.  The engine
+    always passes row_off[pair_q[p]] (a multiple of 256); here the pairs are packed back to back at odd offsets, the same
+    query frame is listed twice, and the arrays end exactly behind the last pair (the filter kernel reads its queries four
+    at a time and must not look past the pair's rows)."""
+    import ctypes as C
+    counts = [301, 257, 4, 7, 130, 513]
+    frames = _ragged_frames(counts, seed=5, dup_coords=True)
+    st = _ingest(engine, frames)
+    pairs = [(1, 0), (2, 1), (3, 2), (4, 0), (5, 4), (1, 5)]
+    dev = engine.device
+    pq = torch.tensor([q for q, _ in pairs], dtype=torch.int32, device=dev)
+    pt = torch.tensor([t for _, t in pairs], dtype=torch.int32, device=dev)
+    offs, o = [], 1
+    for q, _ in pairs:
+        offs.append(o)
+        o += counts[q]
+    rows = o
+    out_off = torch.tensor(offs, dtype=torch.int32, device=dev)
+    P = len(pairs)
+    p_ = lambda t: C.c_void_p(t.data_ptr())
+    top2_idx = torch.full((rows, 2), -7, dtype=torch.int32, device=dev); top2_d2 = torch.full((rows, 2), -7, dtype=torch.int32, device=dev)
+    engine._check(engine.lib.evz_match_top2(engine.h, p_(st.desc), p_(st.ckey), st.rows, p_(st.row_off), p_(st.n_kp), p_(pq), p_(pt),
+                                            p_(out_off), P, p_(top2_idx), p_(top2_d2), engine._stream()))
+    surv = torch.full((rows,), 9, dtype=torch.uint8, device=dev)
+    m_idx = torch.empty((rows, 2), dtype=torch.int32, device=dev); m_pts = torch.empty((rows, 4), dtype=torch.float32, device=dev)
+    m_cnt = torch.empty(P, dtype=torch.int32, device=dev); n_f = torch.empty(P, dtype=torch.int32, device=dev)
+    status = torch.empty(P, dtype=torch.int32, device=dev)
+    engine._check(engine.lib.evz_filter_matches(engine.h, p_(top2_idx), p_(top2_d2), p_(st.coords), p_(st.canon), p_(st.row_off),
+                                                p_(st.n_kp), p_(pq), p_(pt), p_(out_off), P, st.max_kp, 0.5, 4, p_(surv), p_(m_idx),
+                                                p_(m_pts), p_(m_cnt), p_(n_f), p_(status), engine._stream()))
+    torch.cuda.synchronize()
+    assert int(top2_idx[0, 0]) == -7 and int(surv[0]) == 9                      # row 0 belongs to nobody
+    for p, ((qf, tf), o) in enumerate(zip(pairs, offs)):
+        nq = counts[qf]
+        idx, d2 = matching.knn_top2(frames[qf][1], frames[tf][1])
+        assert np.array_equal(top2_idx[o:o + nq].cpu().numpy(), idx), p
+        assert np.array_equal(top2_d2[o:o + nq].cpu().numpy().astype(np.int64), d2), p
+        assert np.array_equal(surv[o:o + nq].cpu().numpy().astype(bool), matching.ratio_survivors(idx, d2)), p
+        mk = matching.match_kps(frames[qf][0], frames[qf][1], frames[tf][0], frames[tf][1])
+        assert int(n_f[p]) == len(mk["matches"]) and int(status[p]) == mk["status"], p
+        m = int(m_cnt[p])
+        assert m == len(mk["pts_a"]), p
+        if m:
+            pts = m_pts[o:o + m].cpu().numpy()
+            assert np.array_equal(pts[:, :2], mk["pts_a"]) and np.array_equal(pts[:, 2:], mk["pts_b"]), p
+
+
 def test_match_golden_sets(engine, golden):
     for i in range(int(golden["knn_n"])):
         q, t = golden[f"knn{i}_q"], golden[f"knn{i}_t"]

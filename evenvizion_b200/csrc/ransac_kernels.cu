@@ -694,6 +694,9 @@ ransac_score_kernel(const FhArgs a, double* __restrict__ Hbest_out, int32_t* __r
     const int64_t o = a.off[p];
     if (st_p != EVZ_ST_OK) return;
     if (m < 4) { if (tid == 0) a.status[p] = EVZ_ST_FEW_POINTS; return; }
+    // max_cnt sizes the shared-memory tables: a pair that exceeds it (the caller's bound was wrong) is reported as
+    // failed, not truncated and not staged past the end of the tables
+    if (m > a.max_cnt) { if (tid == 0) a.status[p] = a.fail_status; return; }
 
     // stage the point pairs (optionally through matrix_H_prev); track max |coordinate|
     const double* T = a.pre_H ? a.pre_H + static_cast<size_t>(p) * 9 : nullptr;

@@ -173,7 +173,7 @@ int evz_filter_matches(evz_handle* h, const int32_t* top2_idx, const int32_t* to
  * utils.py:356-358 (level 2), including the 70 % inlier gate of utils.py:359-360 when
  * min_inlier_frac > 0.  Pairs whose status is non-zero on entry are skipped.
  *   pts        DEV float [rows][4]  point pairs of pair p at rows [off[p], off[p]+cnt[p])
- *   max_cnt    upper bound of cnt[p] (sizes shared memory; <= EVZ_MAX_KP)
+ *   max_cnt    upper bound of cnt[p] (sizes shared memory; <= EVZ_MAX_KP); a pair with cnt[p] > max_cnt gets fail_status
  *   pre_H      DEV double [P][9] or NULL: both point sets are first mapped through this
  *              matrix in f64 and rounded to f32 (utils.py:351-355, matrix_H_prev)
  *   n_hyp      hypotheses per pair (counter-based sampler: seed, pair_id_base + p, level)

@@ -72,9 +72,13 @@ def test_ingest_layout(engine):
         assert np.array_equal(canon[o:o + n], exp)
 
 
-def test_match_ragged_pairs(engine):
-    counts = [300, 333, 257, 1, 0, 600, 128, 129]
-    frames = _ragged_frames(counts, seed=1, dup_coords=True)
+@pytest.mark.parametrize("d,counts", [
+    (128, [300, 333, 257, 1, 0, 600, 128, 129]),
+    (32, [300, 2600, 257, 1, 0, 600, 2048, 129]),          # ORB width: one data K block is multiplied, several train tiles
+    (64, [513, 1, 1030, 255]),                             # two data K blocks
+])
+def test_match_ragged_pairs(engine, d, counts):
+    frames = _ragged_frames(counts, d=d, seed=1, dup_coords=True)
     st = _ingest(engine, frames)
     pq = list(range(1, len(counts)))
     pt = list(range(0, len(counts) - 1))

@@ -226,3 +226,50 @@ def test_find_homography_at_baseline_config_sizes(engine, n, out_frac, n_hyp, le
         inl = ref["mask_best"]
         err = np.linalg.norm(_px(out["H"][i].cpu().numpy(), a[inl]) - _px(ref["H"], a[inl]), axis=1).mean()
         assert err < 1e-3, (i, err)
+
+
+def test_find_homography_degenerate_sets(engine):
+    """Inputs on which most or all hypotheses are rejected or the fit is exact: collinear points (no valid sample: the
+    reference's findHomography returns None -> "can't find homography matrix"), every point repeated three times, an exact
+    translation without noise (all residuals zero: the LM loop must not start), a set whose inliers lie on a line (the
+    winning samples are near-degenerate), coordinates a hundred times larger.  Status, winner, masks against the oracle."""
+    rng = np.random.default_rng(23)
+    n = 400
+    x = rng.permutation(1900)[:n].astype(np.float32)                                      # integers: exactly collinear in f32
+    col_a = np.c_[x, 0.5 * x + 10].astype(np.float32)
+    col = (col_a, (col_a + np.float32([3, -2])).astype(np.float32))                       # all collinear
+    a3, b3 = _mk(rng, 150, 0.2)
+    rep = (np.repeat(a3, 3, 0), np.repeat(b3, 3, 0))                                      # every correspondence three times
+    at = (rng.random((300, 2)) * [1920, 1080]).astype(np.float32)
+    at = np.round(at)                                                                     # exact in f32 after the shift
+    tr = (at, (at + np.float32([5, -7])).astype(np.float32))                              # exact translation, zero residual
+    al, bl = _mk(rng, 500, 0.0)
+    line = rng.random(500) < 0.8
+    al[line, 1] = (0.3 * al[line, 0] + 100).astype(np.float32)                            # 80 % of the points on one line ...
+    bl[line] = (al[line] + np.float32([4, 4])).astype(np.float32)
+    bl[~line] = (al[~line] + np.float32([4, 4]) + rng.normal(size=(int((~line).sum()), 2)) * 0.3).astype(np.float32)
+    big_a, big_b = _mk(rng, 600, 0.3)
+    big = ((big_a * 100).astype(np.float32), (big_b * 100).astype(np.float32))            # 192 000 px wide: no inlier at 3 px but the exact ones
+    sets = [col, rep, tr, (al, bl), big]
+    pts, off, cnt, off_h, cnt_h = _pack(sets, engine.device)
+    status = torch.zeros(len(sets), dtype=torch.int32, device=engine.device)
+    n_hyp, seed, base, level = 512, 3, 7, 1
+    out = engine.find_homography(pts, off, cnt, status, int(cnt_h.max()), n_hyp, seed, base, level, 3.0, 0.0, 4)
+    torch.cuda.synchronize()
+    st = status.cpu().numpy()
+    for i, (a, b) in enumerate(sets):
+        ref = ransac.find_homography_seeded(a, b, n_hyp, seed, base + i, level, 3.0)
+        assert st[i] == ref["status"], (i, st[i], ref["status"])
+        if ref["status"] != 0:
+            continue
+        o, m = off_h[i], cnt_h[i]
+        assert int(out["best_hyp"][i]) == ref["hyp"]["best"] and int(out["best_cnt"][i]) == ref["hyp"]["best_count"], i
+        assert np.array_equal(out["mask_best"][o:o + m].cpu().numpy().astype(bool), ref["mask_best"]), i
+        inl = ref["mask_best"]
+        H = out["H"][i].cpu().numpy()
+        assert np.isfinite(H).all(), i
+        scale = 100.0 if i == 4 else 1.0
+        err = np.linalg.norm(_px(H, a[inl]) - _px(ref["H"], a[inl]), axis=1).mean()
+        assert err < 1e-3 * scale, (i, err)
+    assert st[0] != 0                                                                     # collinear: no model
+    assert st[2] == 0 and int(out["inl_cnt"][2]) == 300                                   # exact translation: every point

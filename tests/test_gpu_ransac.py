@@ -273,3 +273,40 @@ def test_find_homography_degenerate_sets(engine):
         assert err < 1e-3 * scale, (i, err)
     assert st[0] != 0                                                                     # collinear: no model
     assert st[2] == 0 and int(out["inl_cnt"][2]) == 300                                   # exact translation: every point
+
+
+def test_static_filter_rounding_ties_windows(engine):
+    """find_point_displacement / get_largest_group_points corner cases (reference utils.py:258-325): displacements exactly on
+    .5 (Python round = half to even), two bins with the same count (the first-inserted key wins), bins thousands of pixels
+    apart (several histogram windows), and a displacement beyond EVZ_R_MAX (the flag, where the reference's dict would simply
+    hold one more key).  Against the oracle's restatement, which is pinned to the reference's own output."""
+    H = np.eye(3).ravel()
+    def shifted(n, dx, start):
+        a = np.c_[np.arange(start, start + n), np.full(n, 7.0)].astype(np.float32)
+        return a, (a + np.float32([dx, 0])).astype(np.float32)
+    # (1) 2.5 -> 2 and 3.5 -> 4 and 2.0 -> 2: bin 2 collects 5 + 4 points, bin 4 collects 6
+    parts = [shifted(5, 2.5, 0), shifted(6, 3.5, 100), shifted(4, 2.0, 200)]
+    s1 = (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]))
+    # (2) a tie: bins 9 (inserted first), 3 and 5 hold four points each
+    parts = [shifted(4, 9.0, 0), shifted(4, 3.0, 50), shifted(4, 5.0, 90), shifted(2, 1.0, 130)]
+    s2 = (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]))
+    # (3) bins 0, 5000 and 16000: three windows of the histogram, the largest group in the last one
+    parts = [shifted(30, 0.0, 0), shifted(20, 5000.0, 100), shifted(40, 16000.0, 200)]
+    s3 = (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]))
+    # (4) one displacement beyond EVZ_R_MAX = 16383
+    parts = [shifted(10, 4.0, 0), shifted(1, 20000.0, 50)]
+    s4 = (np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts]))
+    sets = [s1, s2, s3, s4]
+    pts, off, cnt, off_h, cnt_h = _pack(sets, engine.device)
+    status = torch.zeros(len(sets), dtype=torch.int32, device=engine.device)
+    Hd = torch.from_numpy(np.tile(H, (len(sets), 1))).to(engine.device)
+    out_pts, out_cnt, best_r, flags = engine.static_filter(pts, off, cnt, Hd, status)
+    torch.cuda.synchronize()
+    want_r = [2, 9, 16000, 4]
+    for i, (a, b) in enumerate(sets):
+        keep, br, bad = static_filter.static_points(H, a, b)
+        assert br == want_r[i], (i, br)
+        assert int(best_r[i]) == br and int(out_cnt[i]) == len(keep) and bool(int(flags[i])) == bad, i
+        g = out_pts[off_h[i]:off_h[i] + len(keep)].cpu().numpy()
+        assert np.array_equal(g[:, :2], a[keep]) and np.array_equal(g[:, 2:], b[keep]), i
+    assert int(out_cnt[0]) == 9 and int(flags[3]) == 1 and int(flags[2]) == 0

@@ -136,6 +136,38 @@ def test_match_compact_output_rows_through_the_c_abi(engine):
             assert np.array_equal(pts[:, :2], mk["pts_a"]) and np.array_equal(pts[:, 2:], mk["pts_b"]), p
 
 
+@pytest.mark.parametrize("ratio,min_pts", [(0.8, 4), (0.3, 4), (0.5, 100000), (1.0, 1), (0.7071067811865476, 4)])
+def test_match_ratio_and_minimum_parameters(engine, ratio, min_pts):
+    """KeyPoints.match_kps(ratio=..., min_matching_pts=...) (matching.py:75, 113-116, 190): the f32-sqrt / f64-compare ratio
+    test at other ratios (1.0 keeps a query only when its two distances differ; sqrt(1/2) puts d0^2 * 2 == d1^2 on the edge),
+    and the minimum that turns a pair into NoMatchesException."""
+    counts = [700, 650, 129]
+    frames = _ragged_frames(counts, seed=9, dup_coords=True)
+    # query row 5 of frame 1 against train rows 0 / 1 of frame 0: d^2 = 50 and 100 (exactly 2 x: the sqrt(1/2) ratio edge)
+    frames[0][1][0] = 0; frames[0][1][1] = 0; frames[0][1][1][:2] = [15, 5]
+    frames[1][1][5] = 0; frames[1][1][5][:2] = [5, 5]
+    idx, d2 = matching.knn_top2(frames[1][1][5:6], frames[0][1])
+    assert idx[0].tolist() == [0, 1] and d2[0].tolist() == [50, 100]
+    st = _ingest(engine, frames)
+    pairs = [(1, 0), (2, 1)]
+    r = engine.match(st, [q for q, _ in pairs], [t for _, t in pairs], ratio, min_pts)
+    torch.cuda.synchronize()
+    for p, (qf, tf) in enumerate(pairs):
+        o = int(st.row_off_h[qf]); nq = counts[qf]
+        mk = matching.match_kps(frames[qf][0], frames[qf][1], frames[tf][0], frames[tf][1], ratio, min_pts)
+        assert np.array_equal(r.surv[o:o + nq].cpu().numpy().astype(bool), mk["surv"]), (ratio, p)
+        assert int(r.n_filtered[p]) == len(mk["matches"]) and int(r.status[p]) == mk["status"], (ratio, p)
+        m = int(r.m_cnt[p])
+        assert m == len(mk["pts_a"])
+        if m:
+            pts = r.m_pts[o:o + m].cpu().numpy()
+            assert np.array_equal(pts[:, :2], mk["pts_a"]) and np.array_equal(pts[:, 2:], mk["pts_b"])
+    if min_pts == 100000:
+        assert int(r.status[0]) == 1 and int(r.m_cnt[0]) == 0
+    if ratio == 1.0:
+        assert int(r.surv[int(st.row_off_h[1]) + 5]) == 1                # 50 < 100
+
+
 def test_match_golden_sets(engine, golden):
     for i in range(int(golden["knn_n"])):
         q, t = golden[f"knn{i}_q"], golden[f"knn{i}_t"]

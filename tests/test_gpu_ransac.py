@@ -310,3 +310,24 @@ def test_static_filter_rounding_ties_windows(engine):
         g = out_pts[off_h[i]:off_h[i] + len(keep)].cpu().numpy()
         assert np.array_equal(g[:, :2], a[keep]) and np.array_equal(g[:, 2:], b[keep]), i
     assert int(out_cnt[0]) == 9 and int(flags[3]) == 1 and int(flags[2]) == 0
+
+
+@pytest.mark.parametrize("thresh", [0.75, 1.0, 5.0, 12.5])
+def test_find_homography_other_thresholds(engine, thresh):
+    """match_static_kps(reproj_thresh=...) (matching.py:131, 156-157): the fused fast path derives its bands from the
+    threshold, so winner and masks must equal the oracle at other thresholds than the reference's default 3.0."""
+    rng = np.random.default_rng(int(thresh * 100))
+    sets = [_mk(rng, 900, 0.3, noise=0.8), _mk(rng, 333, 0.6, noise=1.5), _mk(rng, 1500, 0.1, noise=0.3)]
+    pts, off, cnt, off_h, cnt_h = _pack(sets, engine.device)
+    status = torch.zeros(len(sets), dtype=torch.int32, device=engine.device)
+    out = engine.find_homography(pts, off, cnt, status, int(cnt_h.max()), 768, 5, 11, 1, thresh, 0.0, 4)
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(sets):
+        ref = ransac.find_homography_seeded(a, b, 768, 5, 11 + i, 1, thresh)
+        assert int(status[i]) == ref["status"] == 0, i
+        o, m = off_h[i], cnt_h[i]
+        assert int(out["best_hyp"][i]) == ref["hyp"]["best"] and int(out["best_cnt"][i]) == ref["hyp"]["best_count"], i
+        assert np.array_equal(out["mask_best"][o:o + m].cpu().numpy().astype(bool), ref["mask_best"]), i
+        inl = ref["mask_best"]
+        err = np.linalg.norm(_px(out["H"][i].cpu().numpy(), a[inl]) - _px(ref["H"], a[inl]), axis=1).mean()
+        assert err < 1e-3, (i, err)

@@ -342,3 +342,66 @@ def test_video_geometry_streamed_equals_single_batch(engine):
         assert torch.equal(a.top2_idx[valid], b.top2_idx[valid]) and torch.equal(a.top2_d2[valid], b.top2_d2[valid])
         assert torch.equal(a.m_cnt, b.m_cnt)
         assert torch.equal(a.static_cnt, b.static_cnt) and torch.equal(a.best_hyp2, b.best_hyp2)
+
+
+def test_c_abi_error_codes(engine):
+    """include/evz.h: every entry point returns an int (0 = ok, < 0 = error, no exception crosses the ABI), invalid input is
+    refused with a code and a message instead of being truncated or run on a fallback.  EVZ_E_ARG = -2 for null / misaligned /
+    out-of-range arguments, EVZ_E_UNSUPPORTED = -5 for sizes beyond the shared-memory tables; an empty batch is a no-op."""
+    import ctypes as C
+    import torch
+    lib, h, dev = engine.lib, engine.h, engine.device
+    s = engine._stream()
+    p_ = lambda t: C.c_void_p(t.data_ptr())
+    i32 = lambda *shape: torch.zeros(shape, dtype=torch.int32, device=dev)
+    desc = torch.zeros((512, 128), dtype=torch.uint8, device=dev); ckey = i32(512)
+    row_off = torch.tensor([0, 256, 512], dtype=torch.int32, device=dev); n_kp = torch.tensor([10, 10], dtype=torch.int32, device=dev)
+    pq, pt, oo = i32(1) + 1, i32(1), i32(1) + 256
+    ti, td = i32(512, 2), i32(512, 2)
+    E_ARG, E_UNSUPPORTED = -2, -5
+    msg = lambda: lib.evz_last_error(h).decode()
+    # null pointer
+    assert lib.evz_match_top2(h, None, p_(ckey), 512, p_(row_off), p_(n_kp), p_(pq), p_(pt), p_(oo), 1, p_(ti), p_(td), s) == E_ARG
+    assert "null" in msg()
+    # total_rows not a multiple of 256
+    assert lib.evz_match_top2(h, p_(desc), p_(ckey), 500, p_(row_off), p_(n_kp), p_(pq), p_(pt), p_(oo), 1, p_(ti), p_(td), s) == E_ARG
+    assert "256" in msg()
+    # descriptor bytes out of range (evz_match_top2_d)
+    assert lib.evz_match_top2_d(h, p_(desc), 0, p_(ckey), 512, p_(row_off), p_(n_kp), p_(pq), p_(pt), p_(oo), 1, p_(ti), p_(td), s) == E_ARG
+    assert lib.evz_match_top2_d(h, p_(desc), 129, p_(ckey), 512, p_(row_off), p_(n_kp), p_(pq), p_(pt), p_(oo), 1, p_(ti), p_(td), s) == E_ARG
+    # misaligned descriptor store
+    mis = C.c_void_p(desc.data_ptr() + 16)
+    assert lib.evz_match_top2(h, mis, p_(ckey), 512, p_(row_off), p_(n_kp), p_(pq), p_(pt), p_(oo), 1, p_(ti), p_(td), s) == E_ARG
+    # empty batch: ok, nothing written
+    ti.fill_(-7)
+    assert lib.evz_match_top2(h, p_(desc), p_(ckey), 512, p_(row_off), p_(n_kp), p_(pq), p_(pt), p_(oo), 0, p_(ti), p_(td), s) == 0
+    torch.cuda.synchronize()
+    assert int((ti != -7).sum()) == 0
+    # RANSAC: more points per pair than the shared-memory tables hold, too many hypotheses, null outputs that are required
+    pts = torch.zeros((64, 4), dtype=torch.float32, device=dev); off, cnt, st = i32(1), i32(1) + 8, i32(1)
+    H = torch.zeros((1, 9), dtype=torch.float64, device=dev)
+    fh = lambda max_cnt, n_hyp, Hp: lib.evz_find_homography(h, p_(pts), p_(off), p_(cnt), 1, max_cnt, None, n_hyp, 0, 0, 1, 3.0, 0.0, 4,
+                                                             p_(st), Hp, None, None, None, None, None, None, s)
+    assert fh(12289, 64, p_(H)) == E_UNSUPPORTED and "12288" in msg()
+    assert fh(16, 70000, p_(H)) == E_ARG
+    assert fh(16, 0, p_(H)) == E_ARG
+    assert fh(16, 64, None) == E_ARG
+    # a pair that exceeds the promised max_cnt is reported as failed, not run
+    cnt.fill_(40)
+    assert fh(16, 64, p_(H)) == 0
+    torch.cuda.synchronize()
+    assert int(st[0]) == 4 and float(H.abs().sum()) == 0.0
+    # filter / static filter: frames beyond the supported keypoint count
+    surv = torch.zeros(512, dtype=torch.uint8, device=dev); mi = i32(512, 2); mp = torch.zeros((512, 4), dtype=torch.float32, device=dev)
+    coords = torch.zeros((512, 2), dtype=torch.float32, device=dev); canon = i32(512)
+    assert lib.evz_filter_matches(h, p_(ti), p_(td), p_(coords), p_(canon), p_(row_off), p_(n_kp), p_(pq), p_(pt), p_(oo), 1, 12289,
+                                  0.5, 4, p_(surv), p_(mi), p_(mp), p_(i32(1)), p_(i32(1)), p_(i32(1)), s) == E_UNSUPPORTED
+    assert lib.evz_static_filter(h, p_(pts), p_(off), p_(cnt), 1, 12289, p_(H), p_(st), p_(mp), p_(i32(1)), p_(i32(1)), p_(i32(1)),
+                                 None, s) == E_UNSUPPORTED
+    # scan / remap argument checks
+    assert lib.evz_chain_scan(h, p_(H), p_(st), 1, 1, None, None, None, None, None, s) == E_ARG          # nothing to compute
+    assert lib.evz_chain_seed_apply(h, p_(H), 2, 2, 1, 1, p_(H), None, p_(H), s) == E_ARG               # rank outside [0, world)
+    # the handle is still usable
+    r = engine.match(engine.ingest(np.zeros((8, 128), np.uint8), np.zeros((8, 2), np.float32), [4, 4]), [1], [0])
+    torch.cuda.synchronize()
+    assert int(r.status[0]) in (0, 1)

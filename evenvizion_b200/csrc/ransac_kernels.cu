@@ -2,21 +2,25 @@
 // Replaces cv2.findHomography(a, b, cv2.RANSAC, thresh) (reference matching.py:156-157,
 // utils.py:356-358) and the 70 % gate of compute_homography (utils.py:359-360).
 //
-// ransac_score_kernel (256 threads, one CTA per pair)
-//   phase 1  every thread owns kHpt hypotheses at a time: counter-based PCG sample of 4 distinct
-//            matches, closed-form 4-point solve in f64 registers (projective basis), cast to f32;
-//   phase 2  all matches (float4 ax,ay,bx,by staged in shared memory) are scored against the
-//            thread's hypotheses (broadcast LDS.128, inlier count in a register).  The inlier test is
-//            OpenCV's f32 computeError <= thresh^2 with individually rounded operations.  To avoid
-//            paying ~35 instructions for every evaluation, a fused (FFMA + rcp.approx, ~11
-//            instructions) value is computed first together with a per-hypothesis bound on its
-//            distance from the exactly-rounded value; only evaluations whose fused error lies inside
-//            [t - band, t + band] re-run the exact formula.  Counts are therefore bit-identical to
-//            evaluating the exact formula everywhere (EVZ_OPT_RANSAC_EXACT forces that, for tests);
-//            block arg-max on (count desc, hypothesis asc).
-// ransac_refit_kernel (128 threads, one CTA per pair)
-//   phase 3  inlier mask of the winner (exact formula), then LM on the 8 free parameters in f64
-//            with OpenCV's damping schedule, started from the winning model;
+// ransac_score_kernel (256 threads, one CTA per pair, 4 CTAs per SM)
+//   staging  the pair's point list (float4 ax,ay,bx,by; contiguous, 16-byte aligned) arrives in shared memory by one bulk
+//            copy (cp.async.bulk + mbarrier); with a pre-transform (pre_H) a load loop maps the points on the way;
+//   pass 0   every hypothesis: counter-based PCG sample of 4 distinct matches, closed-form 4-point solve in f64 registers
+//            (projective basis), orientation / collinearity test, ordered compaction of the valid ones; the f32 model of
+//            a valid hypothesis goes to a per-pair model cache in global memory (hyp_model) so that later stages load
+//            32 bytes instead of solving again;
+//   scoring  all matches are scored against the thread's hypotheses (broadcast LDS.128, counts in registers).  The inlier
+//            test is OpenCV's f32 computeError <= thresh^2 with individually rounded operations.  To avoid paying ~35
+//            instructions for every evaluation, a fused (FFMA + rcp.approx, ~11 instructions) value is classified
+//            against per-hypothesis thresholds tlo / thi derived from a rounding-error bound, which gives count bounds
+//            [lo, hi]; only hypotheses whose bounds still matter are rescored with the exact formula (one warp per
+//            hypothesis, ballot / popc).  Level 1 runs in stages over matches partitioned by the leading hypothesis and
+//            drops hypotheses that can no longer win; level 2 searches for the first hypothesis that counts every point.
+//            Counts and the (count desc, hypothesis asc) arg-max are identical to evaluating the exact formula for every
+//            hypothesis (EVZ_OPT_RANSAC_EXACT / EVZ_OPT_RANSAC_NO_PRUNE force that, for the tests).
+// ransac_refit_kernel (64 threads, one CTA per pair that found a model)
+//   phase 3  inlier mask of the winner (exact formula) inside the first pass of an LM refit on the 8 free parameters in
+//            f64 with OpenCV's damping schedule, started undamped from the winning model;
 //   phase 4  final mask = f32 error of the refined H <= thresh^2, inlier count, 70 % gate.
 //
 // This file is compiled with --fmad=false: the f64 solver must round exactly like the NumPy
